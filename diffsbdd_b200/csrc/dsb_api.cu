@@ -1,0 +1,450 @@
+// C ABI of libdiffsbdd_b200.so: parameter table, weight packing, workspace carve-up, forward
+// orchestration (include/diffsbdd_b200.h).  Host logic only + tiny packing kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dsb_internal.cuh"
+
+namespace dsb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- parameter table (reference state_dict order of diffsbdd_b200/synthetic.py::state_dict_spec) -------
+struct ParamInfo { std::string name; int64_t numel; int rows, cols; };
+
+static int validate(const dsb_config* c) {
+  if (!c) { set_error("null config"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (c->n_dims != 3) { set_error("n_dims must be 3"); return DSB_ERR_UNSUPPORTED_CONFIG; }
+  if (c->hidden_nf != 64 && c->hidden_nf != 128 && c->hidden_nf != 192 && c->hidden_nf != 256) {
+    set_error("hidden_nf=%d unsupported (64,128,192,256)", c->hidden_nf); return DSB_ERR_UNSUPPORTED_CONFIG;
+  }
+  if (c->n_layers < 1 || c->n_layers > kMaxLayers || c->inv_sublayers < 1 || c->inv_sublayers > kMaxSub) {
+    set_error("n_layers/inv_sublayers out of range"); return DSB_ERR_UNSUPPORTED_CONFIG;
+  }
+  if (c->atom_nf < 1 || c->residue_nf < 1 || c->joint_nf < 1 || c->atom_nf > 64 || c->residue_nf > 64 ||
+      c->joint_nf > 1024 || c->edge_embedding_dim < 0 || c->edge_embedding_dim > 64) {
+    set_error("feature sizes out of range"); return DSB_ERR_UNSUPPORTED_CONFIG;
+  }
+  if (!(c->normalization_factor > 0.f)) { set_error("normalization_factor must be > 0"); return DSB_ERR_INVALID_ARGUMENT; }
+  return 0;
+}
+
+static std::vector<ParamInfo> param_table(const dsb_config& c) {
+  std::vector<ParamInfo> v;
+  const int A = c.atom_nf, R = c.residue_nf, J = c.joint_nf, H = c.hidden_nf;
+  const int Din = J + (c.condition_time ? 1 : 0), F = 2 + c.edge_embedding_dim;
+  auto lin = [&](const std::string& p, int out_f, int in_f, bool bias = true) {
+    v.push_back({p + ".weight", (int64_t)out_f * in_f, out_f, in_f});
+    if (bias) v.push_back({p + ".bias", out_f, out_f, 1});
+  };
+  lin("atom_encoder.0", 2 * A, A); lin("atom_encoder.2", J, 2 * A);
+  lin("atom_decoder.0", 2 * A, J); lin("atom_decoder.2", A, 2 * A);
+  lin("residue_encoder.0", 2 * R, R); lin("residue_encoder.2", J, 2 * R);
+  lin("residue_decoder.0", 2 * R, J); lin("residue_decoder.2", R, 2 * R);
+  if (c.edge_embedding_dim > 0) v.push_back({"edge_embedding.weight", (int64_t)3 * c.edge_embedding_dim, 3, c.edge_embedding_dim});
+  lin("egnn.embedding", H, Din); lin("egnn.embedding_out", Din, H);
+  for (int k = 0; k < c.n_layers; ++k) {
+    const std::string b = "egnn.e_block_" + std::to_string(k);
+    for (int s = 0; s < c.inv_sublayers; ++s) {
+      const std::string g = b + ".gcl_" + std::to_string(s);
+      lin(g + ".edge_mlp.0", H, 2 * H + F); lin(g + ".edge_mlp.2", H, H);
+      lin(g + ".node_mlp.0", H, 2 * H); lin(g + ".node_mlp.2", H, H);
+      if (c.attention) lin(g + ".att_mlp.0", 1, H);
+    }
+    const std::string q = b + ".gcl_equiv";
+    lin(q + ".coord_mlp.0", H, 2 * H + F); lin(q + ".coord_mlp.2", H, H); lin(q + ".coord_mlp.4", 1, H, false);
+    if (!c.reflection_equivariant) { lin(q + ".cross_product_mlp.0", H, 2 * H + F); lin(q + ".cross_product_mlp.2", H, H); }
+  }
+  return v;
+}
+
+// ---- packing kernels -----------------------------------------------------------------------------------
+// dst[k*ldd + dcol + n] = src[n*lds + scol + k]   for n < N, k < K
+__global__ void pack_T_kernel(float* dst, int ldd, int dcol, const float* src, int lds, int scol, int N, int K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * K) return;
+  const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K);
+  dst[(size_t)k * ldd + dcol + n] = src[(size_t)n * lds + scol + k];
+}
+__global__ void pack_copy_kernel(float* dst, const float* src, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) dst[idx] = src[idx];
+}
+// tb[t][n] = sum_e W1[n][scol + e] * emb[t][e]
+__global__ void pack_tb_kernel(float* dst, const float* w1, int lds, int scol, const float* emb, int De, int H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * H) return;
+  const int t = idx / H, n = idx - t * H;
+  float acc = 0.f;
+  for (int e = 0; e < De; ++e) acc = fmaf(w1[(size_t)n * lds + scol + e], emb[t * De + e], acc);
+  dst[idx] = acc;
+}
+
+struct Packer {
+  float* blob; size_t used = 0; bool dry;
+  explicit Packer(float* b) : blob(b), dry(b == nullptr) {}
+  float* alloc(size_t n) { size_t o = used; used += (n + 63) & ~size_t(63); return dry ? nullptr : blob + o; }
+  const float* T(const float* src, int lds, int scol, int N, int K, float* dst, int ldd, int dcol) {
+    if (!dry) { int64_t tot = (int64_t)N * K; pack_T_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(dst, ldd, dcol, src, lds, scol, N, K); }
+    return dst;
+  }
+  const float* copy(const float* src, int64_t n) {
+    float* d = alloc(n);
+    if (!dry) pack_copy_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d, src, n);
+    return d;
+  }
+};
+
+static int pack_weights(dsb_dynamics* d, const float* const* params, const std::vector<ParamInfo>& tab, bool dry,
+                        size_t* floats_out) {
+  const dsb_config& c = d->cfg;
+  const int H = c.hidden_nf, J = c.joint_nf, Din = J + (c.condition_time ? 1 : 0), De = c.edge_embedding_dim;
+  const int F = 2 + De, ld1 = 2 * H + F;
+  std::map<std::string, int> index;
+  for (size_t i = 0; i < tab.size(); ++i) index[tab[i].name] = (int)i;
+  auto P = [&](const std::string& n) -> const float* { return dry ? nullptr : params[index.at(n)]; };
+  auto numel = [&](const std::string& n) { return tab[index.at(n)].numel; };
+  Packer pk(dry ? nullptr : d->blob);
+  PackedWeights& w = d->w;
+  auto cp = [&](const std::string& n) { return pk.copy(P(n), numel(n)); };
+
+  w.aenc0_w = cp("atom_encoder.0.weight"); w.aenc0_b = cp("atom_encoder.0.bias");
+  w.aenc2_w = cp("atom_encoder.2.weight"); w.aenc2_b = cp("atom_encoder.2.bias");
+  w.renc0_w = cp("residue_encoder.0.weight"); w.renc0_b = cp("residue_encoder.0.bias");
+  w.renc2_w = cp("residue_encoder.2.weight"); w.renc2_b = cp("residue_encoder.2.bias");
+  w.adec0_w = cp("atom_decoder.0.weight"); w.adec0_b = cp("atom_decoder.0.bias");
+  w.adec2_w = cp("atom_decoder.2.weight"); w.adec2_b = cp("atom_decoder.2.bias");
+  w.rdec0_w = cp("residue_decoder.0.weight"); w.rdec0_b = cp("residue_decoder.0.bias");
+  w.rdec2_w = cp("residue_decoder.2.weight"); w.rdec2_b = cp("residue_decoder.2.bias");
+  { float* t = pk.alloc((size_t)Din * H); w.emb_wT = pk.T(P("egnn.embedding.weight"), Din, 0, H, Din, t, H, 0); }
+  w.emb_b = cp("egnn.embedding.bias");
+  { float* t = pk.alloc((size_t)H * Din); w.out_wT = pk.T(P("egnn.embedding_out.weight"), H, 0, Din, H, t, Din, 0); }
+  w.out_b = cp("egnn.embedding_out.bias");
+  const float* emb = De > 0 ? P("edge_embedding.weight") : nullptr;
+
+  auto first_layer = [&](const std::string& pre, float* W1dst, int ldd, int dcol, float* b1dst,
+                         const float** wr, const float** wr0, const float** tb) {
+    const float* W1 = P(pre + ".weight");
+    pk.T(W1, ld1, 0, H, H, W1dst, ldd, dcol);          // receiver part  (h[row], egnn_new.py:35/99)
+    pk.T(W1, ld1, H, H, H, W1dst, ldd, dcol + H);      // sender part    (h[col])
+    if (!dry) pack_copy_kernel<<<(H + 255) / 256, 256>>>(b1dst + dcol, P(pre + ".bias"), H);
+    float* r = pk.alloc(H); pk.T(W1, ld1, 2 * H, H, 1, r, H, 0); *wr = r;
+    float* r0 = pk.alloc(H); pk.T(W1, ld1, 2 * H + 1, H, 1, r0, H, 0); *wr0 = r0;
+    if (De > 0) {
+      float* t = pk.alloc((size_t)3 * H);
+      if (!dry) pack_tb_kernel<<<(3 * H + 255) / 256, 256>>>(t, W1, ld1, 2 * H + 2, emb, De, H);
+      *tb = t;
+    } else {
+      *tb = nullptr;
+    }
+  };
+
+  for (int k = 0; k < c.n_layers; ++k) {
+    const std::string b = "egnn.e_block_" + std::to_string(k);
+    for (int s = 0; s < c.inv_sublayers; ++s) {
+      const std::string g = b + ".gcl_" + std::to_string(s);
+      GclW& G = w.gcl[k][s];
+      float* W1 = pk.alloc((size_t)H * 2 * H); float* b1 = pk.alloc(2 * H);
+      first_layer(g + ".edge_mlp.0", W1, 2 * H, 0, b1, &G.wr, &G.wr0, &G.tb);
+      G.W1ab = W1; G.b1ab = b1;
+      { float* t = pk.alloc((size_t)H * H); G.W2 = pk.T(P(g + ".edge_mlp.2.weight"), H, 0, H, H, t, H, 0); }
+      G.b2 = cp(g + ".edge_mlp.2.bias");
+      if (c.attention) { G.wa = cp(g + ".att_mlp.0.weight"); G.ba = cp(g + ".att_mlp.0.bias"); }
+      else { G.wa = nullptr; G.ba = nullptr; }
+      { float* t = pk.alloc((size_t)2 * H * H); G.W3 = pk.T(P(g + ".node_mlp.0.weight"), 2 * H, 0, H, 2 * H, t, H, 0); }
+      G.b3 = cp(g + ".node_mlp.0.bias");
+      { float* t = pk.alloc((size_t)H * H); G.W4 = pk.T(P(g + ".node_mlp.2.weight"), H, 0, H, H, t, H, 0); }
+      G.b4 = cp(g + ".node_mlp.2.bias");
+    }
+    const std::string q = b + ".gcl_equiv";
+    EquivW& Q = w.eq[k];
+    const int nm = c.reflection_equivariant ? 1 : 2;
+    float* W1 = pk.alloc((size_t)H * nm * 2 * H); float* b1 = pk.alloc((size_t)nm * 2 * H);
+    const char* names[2] = {".coord_mlp", ".cross_product_mlp"};
+    for (int m = 0; m < 2; ++m) {
+      if (m < nm) {
+        first_layer(q + names[m] + ".0", W1, nm * 2 * H, m * 2 * H, b1, &Q.wr[m], &Q.wr0[m], &Q.tb[m]);
+        float* t = pk.alloc((size_t)H * H);
+        Q.W2[m] = pk.T(P(q + names[m] + ".2.weight"), H, 0, H, H, t, H, 0);
+        Q.b2[m] = cp(q + names[m] + ".2.bias");
+      } else {
+        Q.wr[m] = Q.wr0[m] = Q.tb[m] = Q.W2[m] = Q.b2[m] = nullptr;
+      }
+    }
+    Q.W1 = W1; Q.b1 = b1;
+    Q.w3 = cp(q + ".coord_mlp.4.weight");
+  }
+  *floats_out = pk.used;
+  return 0;
+}
+
+// ---- workspace --------------------------------------------------------------------------------------------
+static Workspace carve(const dsb_config& c, int64_t NL, int64_t NP, int64_t B, int64_t Ecap, void* base) {
+  Workspace ws;
+  const int64_t N = NL + NP;
+  const int H = c.hidden_nf;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return base ? (char*)base + o : (char*)nullptr; };
+  ws.lig_off = (int32_t*)take(sizeof(int32_t) * (B + 2));
+  ws.poc_off = (int32_t*)take(sizeof(int32_t) * (B + 2));
+  ws.gid = (int32_t*)take(sizeof(int32_t) * (N + 1));
+  for (int i = 0; i < 3; ++i) ws.xbuf[i] = (float4*)take(sizeof(float4) * (N + 1));
+  ws.cent = (float4*)take(sizeof(float4) * (B + 1));
+  ws.xagg = (float4*)take(sizeof(float4) * (N + 1));
+  ws.velmean = (float4*)take(sizeof(float4) * (B + 1));
+  ws.h = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
+  ws.hT = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
+  ws.agg = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
+  ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 4 * H);
+  ws.deg = (int32_t*)take(sizeof(int32_t) * (N + 1));
+  ws.row_ptr = (int32_t*)take(sizeof(int32_t) * (N + 2));
+  ws.erow = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + 1));
+  ws.ecol = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + 1));
+  ws.ed0 = (float*)take(sizeof(float) * (size_t)(Ecap + 1));
+  ws.bytes = off;
+  return ws;
+}
+
+static int check_sizes(int64_t NL, int64_t NP, int64_t B, int64_t Ecap) {
+  if (NL < 0 || NP < 0 || B < 0 || Ecap < 0 || NL + NP > (int64_t)1 << 30 || Ecap > ((int64_t)1 << 31) - 256) {
+    set_error("sizes out of range (n_atoms=%lld n_residues=%lld n_graphs=%lld edge_capacity=%lld)", (long long)NL,
+              (long long)NP, (long long)B, (long long)Ecap);
+    return DSB_ERR_INVALID_ARGUMENT;
+  }
+  return 0;
+}
+
+// ---- fused DDPM ligand update --------------------------------------------------------------------------
+__device__ __forceinline__ int lb64(const int64_t* a, int n, int64_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) ddpm_update_kernel(const float* __restrict__ z, const float* __restrict__ eps,
+                                                           const float* __restrict__ noise, const float* __restrict__ coef,
+                                                           const int64_t* __restrict__ mask_atoms, const int64_t* __restrict__ mask_res,
+                                                           const float* __restrict__ pocket, int NL, int NP, int A, int R,
+                                                           float* __restrict__ z_out, float* __restrict__ pocket_out) {
+  const int g = blockIdx.x;
+  const int l0 = lb64(mask_atoms, NL, g), l1 = lb64(mask_atoms, NL, (int64_t)g + 1);
+  const int p0 = lb64(mask_res, NP, g), p1 = lb64(mask_res, NP, (int64_t)g + 1);
+  const int D = 3 + A, DR = 3 + R;
+  const float alpha = coef[g * 3 + 0], cb = coef[g * 3 + 1], sigma = coef[g * 3 + 2];
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int idx = l0 * D + threadIdx.x; idx < l1 * D; idx += blockDim.x) {
+    const float mu = z[idx] / alpha - cb * eps[idx];          // conditional_model.py:451-453
+    const float v = mu + sigma * noise[idx];                   // conditional_model.py:151
+    z_out[idx] = v;
+    const int c = idx % D;
+    if (c < 3) s[c] += v;
+  }
+  __shared__ float red[3][4];
+  __shared__ float com[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s[0]; red[1][threadIdx.x >> 5] = s[1]; red[2][threadIdx.x >> 5] = s[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const float cnt = (l1 - l0) > 0 ? (float)(l1 - l0) : 1.f;
+    com[threadIdx.x] = (red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]) / cnt;
+  }
+  __syncthreads();
+  for (int i = l0 + threadIdx.x; i < l1; i += blockDim.x) {     // conditional_model.py:694
+    z_out[(size_t)i * D + 0] -= com[0]; z_out[(size_t)i * D + 1] -= com[1]; z_out[(size_t)i * D + 2] -= com[2];
+  }
+  for (int idx = p0 * DR + threadIdx.x; idx < p1 * DR; idx += blockDim.x) {   // conditional_model.py:695
+    const int c = idx % DR;
+    const float v = pocket[idx];
+    pocket_out[idx] = c < 3 ? v - com[c] : v;
+  }
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" {
+
+const char* dsb_last_error(void) { return g_err; }
+const char* dsb_version(void) { return "diffsbdd_b200 0.1 (sm_100a, fp32 SIMT edge kernels)"; }
+
+int dsb_param_count(const dsb_config* cfg) {
+  if (int e = validate(cfg)) return e;
+  return (int)param_table(*cfg).size();
+}
+
+int64_t dsb_param_name(const dsb_config* cfg, int i, char* buf, size_t buflen) {
+  if (int e = validate(cfg)) return e;
+  auto tab = param_table(*cfg);
+  if (i < 0 || i >= (int)tab.size() || !buf || buflen == 0) { set_error("param index out of range"); return DSB_ERR_INVALID_ARGUMENT; }
+  snprintf(buf, buflen, "%s", tab[i].name.c_str());
+  return tab[i].numel;
+}
+
+int dsb_dynamics_create(const dsb_config* cfg, const float* const* params, int n_params, dsb_dynamics** out) {
+  if (!out) { set_error("null out"); return DSB_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  if (int e = validate(cfg)) return e;
+  auto tab = param_table(*cfg);
+  if (!params || n_params != (int)tab.size()) { set_error("expected %d parameters, got %d", (int)tab.size(), n_params); return DSB_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < n_params; ++i)
+    if (!params[i]) { set_error("parameter %d (%s) is null", i, tab[i].name.c_str()); return DSB_ERR_INVALID_ARGUMENT; }
+  dsb_dynamics* d = new dsb_dynamics();
+  d->cfg = *cfg;
+  size_t floats = 0;
+  pack_weights(d, params, tab, /*dry=*/true, &floats);
+  d->blob_floats = floats;
+  cudaError_t ce = cudaMalloc(&d->blob, floats * sizeof(float));
+  if (ce != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", floats * sizeof(float), cudaGetErrorString(ce)); delete d; return DSB_ERR_CUDA; }
+  cudaMemset(d->blob, 0, floats * sizeof(float));
+  pack_weights(d, params, tab, /*dry=*/false, &floats);
+  ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (ce != cudaSuccess) { set_error("weight packing failed: %s", cudaGetErrorString(ce)); cudaFree(d->blob); delete d; return DSB_ERR_CUDA; }
+  int dev = 0; cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (int e = configure_edge_kernels(cfg->hidden_nf)) { cudaFree(d->blob); delete d; return e; }
+  *out = d;
+  return 0;
+}
+
+void dsb_dynamics_destroy(dsb_dynamics* dyn) {
+  if (!dyn) return;
+  cudaDeviceSynchronize();
+  cudaFree(dyn->blob);
+  delete dyn;
+}
+
+int64_t dsb_edge_capacity(const int64_t* n_lig, const int64_t* n_pocket, int n_graphs) {
+  int64_t tot = 0;
+  for (int g = 0; g < n_graphs; ++g) { const int64_t n = n_lig[g] + n_pocket[g]; tot += n * n; }
+  return tot;
+}
+
+size_t dsb_dynamics_workspace_bytes(const dsb_dynamics* dyn, int64_t n_atoms, int64_t n_residues, int64_t n_graphs,
+                                    int64_t edge_capacity) {
+  if (!dyn || check_sizes(n_atoms, n_residues, n_graphs, edge_capacity)) return 0;
+  return carve(dyn->cfg, n_atoms, n_residues, n_graphs, edge_capacity, nullptr).bytes + 256;
+}
+
+static int setup(dsb_dynamics* dyn, int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int64_t edge_capacity,
+                 void* workspace, size_t workspace_bytes, Dims* dm, Workspace* ws) {
+  if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (int e = check_sizes(n_atoms, n_residues, n_graphs, edge_capacity)) return e;
+  if (!workspace) { set_error("null workspace"); return DSB_ERR_INVALID_ARGUMENT; }
+  char* base = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  *ws = carve(dyn->cfg, n_atoms, n_residues, n_graphs, edge_capacity, base);
+  if ((size_t)(base - (char*)workspace) + ws->bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", ws->bytes + 256, workspace_bytes);
+    return DSB_ERR_WORKSPACE_TOO_SMALL;
+  }
+  dm->NL = (int)n_atoms; dm->NP = (int)n_residues; dm->N = (int)(n_atoms + n_residues); dm->B = (int)n_graphs;
+  dm->Ecap = edge_capacity;
+  dm->n_coord_rows = dyn->cfg.update_pocket_coords ? dm->N : dm->NL;
+  return 0;
+}
+
+int dsb_dynamics_edges(dsb_dynamics* dyn, const float* xh_atoms, const float* xh_residues, const int64_t* mask_atoms,
+                       const int64_t* mask_residues, int64_t n_atoms, int64_t n_residues, int64_t n_graphs,
+                       int64_t edge_capacity, int32_t* rows, int32_t* cols, int32_t* n_edges, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  Dims dm; Workspace ws;
+  if (int e = setup(dyn, n_atoms, n_residues, n_graphs, edge_capacity, workspace, workspace_bytes, &dm, &ws)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dm.N == 0) { DSB_CUDA_OK(cudaMemsetAsync(n_edges, 0, sizeof(int32_t), s)); return 0; }
+  if (int e = launch_plan(dyn, dm, ws, mask_atoms, mask_residues, s)) return e;
+  if (int e = launch_prep(dyn, dm, ws, xh_atoms, xh_residues, nullptr, 0, mask_atoms, mask_residues, true, s)) return e;
+  ws.erow = rows; ws.ecol = cols;
+  if (int e = launch_edges(dyn, dm, ws, nullptr, s)) return e;
+  DSB_CUDA_OK(cudaMemcpyAsync(n_edges, ws.row_ptr + dm.N, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* xh_residues, const float* t,
+                         int64_t t_numel, const int64_t* mask_atoms, const int64_t* mask_residues, int64_t n_atoms,
+                         int64_t n_residues, int64_t n_graphs, int64_t edge_capacity, float* out_atoms,
+                         float* out_residues, void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+  Dims dm; Workspace ws;
+  if (int e = setup(dyn, n_atoms, n_residues, n_graphs, edge_capacity, workspace, workspace_bytes, &dm, &ws)) return e;
+  const dsb_config& c = dyn->cfg;
+  if (c.condition_time && !(t_numel == 1 || t_numel == n_graphs)) {
+    set_error("t must have 1 or n_graphs=%lld elements, got %lld", (long long)n_graphs, (long long)t_numel);
+    return DSB_ERR_INVALID_ARGUMENT;
+  }
+  if (!status || (!out_atoms && n_atoms) || (!out_residues && n_residues)) { set_error("null output/status"); return DSB_ERR_INVALID_ARGUMENT; }
+  cudaStream_t s = (cudaStream_t)stream;
+  int launches = 0;
+  dyn->last_launches = 0;
+  if (dm.N == 0) return 0;
+  const int H = c.hidden_nf;
+  const int nm = c.reflection_equivariant ? 1 : 2;
+  const size_t hbytes = sizeof(float) * (size_t)dm.N * H;
+
+  if (int e = launch_plan(dyn, dm, ws, mask_atoms, mask_residues, s)) return e; launches += 1;
+  if (int e = launch_prep(dyn, dm, ws, xh_atoms, xh_residues, t, t_numel, mask_atoms, mask_residues, false, s)) return e; launches += 1;
+  if (int e = launch_edges(dyn, dm, ws, status, s)) return e; launches += 3;
+  const float4* xcur = ws.xbuf[0];
+  if (nm == 2) { if (int e = launch_coord_finish(dyn, dm, ws, xcur, nullptr, false, s)) return e; launches += 1; }
+
+  for (int l = 0; l < c.n_layers; ++l) {
+    for (int sub = 0; sub < c.inv_sublayers; ++sub) {
+      const GclW& G = dyn->w.gcl[l][sub];
+      GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0};
+      if (int e = launch_node_gemm(g1, s)) return e;
+      DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
+      if (int e = launch_edge_gcl(dyn, dm, ws, G, xcur, s)) return e;
+      // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
+      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1};
+      if (int e = launch_node_gemm(g2, s)) return e;
+      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0};
+      if (int e = launch_node_gemm(g3, s)) return e;
+      launches += 5;
+    }
+    const EquivW& Q = dyn->w.eq[l];
+    GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, nm * 2 * H, Q.b1, nullptr, 0, ws.P, nm * 2 * H, dm.N, nm * 2 * H, 0};
+    if (int e = launch_node_gemm(g4, s)) return e;
+    DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
+    if (int e = launch_edge_coord(dyn, dm, ws, Q, xcur, s)) return e;
+    float4* xnext = ws.xbuf[1 + (l & 1)];
+    if (int e = launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s)) return e;
+    xcur = xnext;
+    launches += 4;
+  }
+  if (int e = launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s)) return e;
+  launches += 1 + (c.update_pocket_coords ? 1 : 0);
+  dyn->last_launches = launches;
+  return 0;
+}
+
+int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn) { return dyn ? dyn->last_launches : 0; }
+
+int dsb_ddpm_ligand_update(const float* z_lig, const float* eps_hat, const float* noise, const float* coef,
+                           const int64_t* mask_atoms, const int64_t* mask_residues, const float* xh_pocket,
+                           int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int32_t atom_nf, int32_t residue_nf,
+                           float* z_out, float* xh_pocket_out, void* stream) {
+  if (n_graphs <= 0) return 0;
+  if (!z_lig || !eps_hat || !noise || !coef || !mask_atoms || !mask_residues || !xh_pocket || !z_out || !xh_pocket_out) {
+    set_error("null pointer"); return DSB_ERR_INVALID_ARGUMENT;
+  }
+  ddpm_update_kernel<<<(unsigned)n_graphs, 128, 0, (cudaStream_t)stream>>>(z_lig, eps_hat, noise, coef, mask_atoms, mask_residues,
+                                                                          xh_pocket, (int)n_atoms, (int)n_residues, atom_nf,
+                                                                          residue_nf, z_out, xh_pocket_out);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Internal declarations shared by the translation units of libdiffsbdd_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/diffsbdd_b200.h"
+
+namespace dsb {
+
+constexpr int kMaxSub = 4;      // inv_sublayers supported per block
+constexpr int kMaxLayers = 16;
+
+// ---- packed weights (device pointers into one blob; all GEMM operands k-major: W[k][n]) -------------
+struct GclW {            // one GCL (reference egnn_new.py:6-66)
+  const float* W1ab;     // [H][2H]  cols 0..H-1: edge_mlp.0.weight[:, 0:H]^T (receiver h_i), H..2H-1: [:, H:2H]^T (sender h_j)
+  const float* b1ab;     // [2H]     (edge_mlp.0.bias | 0)
+  const float* wr;       // [H]      edge_mlp.0.weight[:, 2H]   (coefficient of current d^2)
+  const float* wr0;      // [H]      edge_mlp.0.weight[:, 2H+1] (coefficient of input-geometry d^2)
+  const float* tb;       // [3][H]   edge_mlp.0.weight[:, 2H+2:] @ edge_embedding[type]  (nullptr without embedding)
+  const float* W2;       // [H][H]   edge_mlp.2.weight^T
+  const float* b2;       // [H]
+  const float* wa;       // [H]      att_mlp.0.weight (nullptr without attention)
+  const float* ba;       // [1]
+  const float* W3;       // [2H][H]  node_mlp.0.weight^T (rows 0..H-1 multiply h, H..2H-1 multiply agg)
+  const float* b3;       // [H]
+  const float* W4;       // [H][H]   node_mlp.2.weight^T
+  const float* b4;       // [H]
+};
+
+struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); index 0 = coord_mlp, 1 = cross_product_mlp
+  const float* W1;       // [H][nm*2H] (coord recv | coord send | cross recv | cross send)
+  const float* b1;       // [nm*2H]    (bias | 0 | bias | 0)
+  const float* wr[2];
+  const float* wr0[2];
+  const float* tb[2];
+  const float* W2[2];    // [H][H]
+  const float* b2[2];    // [H]
+  const float* w3;       // [H] shared bias-free last layer (egnn_new.py:78)
+};
+
+struct PackedWeights {
+  // encoders / decoders keep the reference [out][in] layout (tiny)
+  const float *aenc0_w, *aenc0_b, *aenc2_w, *aenc2_b;
+  const float *renc0_w, *renc0_b, *renc2_w, *renc2_b;
+  const float *adec0_w, *adec0_b, *adec2_w, *adec2_b;
+  const float *rdec0_w, *rdec0_b, *rdec2_w, *rdec2_b;
+  const float *emb_wT, *emb_b;      // [Din][H] k-major, [H]
+  const float *out_wT, *out_b;      // [H][Din] k-major, [Din]
+  GclW gcl[kMaxLayers][kMaxSub];
+  EquivW eq[kMaxLayers];
+};
+
+// ---- workspace carve-up ---------------------------------------------------------------------------
+struct Workspace {
+  int32_t *lig_off, *poc_off;   // [B+1]
+  int32_t *gid;                 // [N]
+  float4 *xbuf[3];              // [N] (x,y,z,0): input, ping, pong
+  float4 *cent;                 // [B]
+  float4 *xagg;                 // [N] raw segment sums of trans
+  float4 *velmean;              // [B]
+  float *h, *hT, *agg, *P;      // [N][H], [N][H], [N][H], [N][4H]
+  int32_t *deg, *row_ptr;       // [N], [N+1]
+  int32_t *erow, *ecol;         // [Ecap]
+  float *ed0;                   // [Ecap]
+  size_t bytes;
+};
+
+struct Dims {
+  int NL, NP, N, B;
+  int64_t Ecap;
+  int n_coord_rows;   // rows whose coordinates move: NL (conditional) or N (joint)
+};
+
+}  // namespace dsb
+
+struct dsb_dynamics {
+  dsb_config cfg;
+  dsb::PackedWeights w;
+  float* blob = nullptr;
+  size_t blob_floats = 0;
+  int num_sms = 148;
+  int last_launches = 0;
+};
+
+namespace dsb {
+
+void set_error(const char* fmt, ...);
+
+#define DSB_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      dsb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DSB_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+// ---- launchers implemented in dsb_node.cu ----------------------------------------------------------
+struct GemmArgs {
+  const float* A1; int lda1; int K1;
+  const float* A2; int lda2; int K2; float div2;   // columns K1..K1+K2-1 come from A2 / div2 (exact division)
+  const float* W; int ldw;                          // k-major [K1+K2][ldw]
+  const float* bias;                                // [Nn] or nullptr
+  const float* R; int ldr;                          // residual (added after bias) or nullptr
+  float* C; int ldc;
+  int M; int Nn; int act;                           // act: 0 none, 1 SiLU
+};
+int launch_node_gemm(const GemmArgs& a, cudaStream_t s);
+
+int launch_plan(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const int64_t* mask_atoms,
+                const int64_t* mask_residues, cudaStream_t s);
+int launch_prep(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const float* xh_atoms,
+                const float* xh_residues, const float* t, int64_t t_numel, const int64_t* mask_atoms,
+                const int64_t* mask_residues, bool coords_only, cudaStream_t s);
+int launch_edges(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, int32_t* status, cudaStream_t s);
+int launch_coord_finish(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const float4* x_old,
+                        float4* x_new, bool apply_update, cudaStream_t s);
+int launch_post(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const float4* x_final,
+                float* out_atoms, float* out_residues, int32_t* status, cudaStream_t s);
+
+// ---- launchers implemented in dsb_edge.cu ----------------------------------------------------------
+int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w,
+                    const float4* x, cudaStream_t s);
+int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w,
+                      const float4* x, cudaStream_t s);
+int configure_edge_kernels(int H);
+
+// ---- device math helpers ----------------------------------------------------------------------------
+// SiLU / sigmoid via MUFU.EX2 + MUFU.RCP: relative error ~2 ulp + |x|*6e-8 from the exponent scaling,
+// i.e. at the fp32 noise floor of the reference itself (3e-7).
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+
+}  // namespace dsb

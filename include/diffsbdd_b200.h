@@ -1,0 +1,145 @@
+/*
+ * diffsbdd_b200 — C ABI of the B200-native DiffSBDD denoiser hot path.
+ *
+ * The reference has no FFI: its "plugin point" is the Python call
+ *     EGNNDynamics.forward(xh_atoms, xh_residues, t, mask_atoms, mask_residues)
+ * (reference equivariant_diffusion/dynamics.py:87-167) made once per DDPM step from
+ * ConditionalDDPM.sample_p_zs_given_zt (conditional_model.py:445) and
+ * EnVariationalDiffusion.sample_p_zs_given_zt (en_diffusion.py:503-557).
+ * The entry points below are what a ctypes binding of that call needs: plain device pointers and
+ * sizes, no torch types.  INTEGRATION.md shows the reference-side stub.
+ *
+ * All `const float*` / `float*` / `int64_t*` arguments are DEVICE pointers unless stated otherwise.
+ * Every function returns 0 on success or a negative dsb_status; dsb_last_error() gives the text.
+ * All kernels are launched on the caller's stream; no function synchronises the stream except
+ * dsb_dynamics_create/destroy (weight packing) — forward is CUDA-graph capturable.
+ */
+#ifndef DIFFSBDD_B200_H_
+#define DIFFSBDD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DSB_OK = 0,
+  DSB_ERR_INVALID_ARGUMENT = -1,
+  DSB_ERR_UNSUPPORTED_CONFIG = -2, /* sin_embedding, aggregation 'mean', mode 'gnn_dynamics', H not in {64..256 step 64} */
+  DSB_ERR_CUDA = -3,
+  DSB_ERR_WORKSPACE_TOO_SMALL = -4
+} dsb_status;
+
+/* Constructor arguments of EGNNDynamics (dynamics.py:11-19); same names, C types.
+ * Cut-offs: a negative value means "None" (no cut-off for that block, dynamics.py:174-181). */
+typedef struct {
+  int32_t atom_nf;               /* dynamics.py:11 */
+  int32_t residue_nf;
+  int32_t n_dims;                /* must be 3 */
+  int32_t joint_nf;
+  int32_t hidden_nf;
+  int32_t n_layers;
+  int32_t inv_sublayers;
+  int32_t attention;             /* bool */
+  int32_t tanh;                  /* bool */
+  int32_t condition_time;        /* bool */
+  int32_t update_pocket_coords;  /* bool: joint model (dynamics.py:130-132, :161-164) */
+  int32_t reflection_equivariant;/* bool: 0 -> cross-product MLP active (egnn_new.py:86-92) */
+  int32_t edge_embedding_dim;    /* 0 = None (dynamics.py:51-53) */
+  float norm_constant;           /* egnn_new.py:301, :315 */
+  float normalization_factor;    /* egnn_new.py:327-328 ('sum' aggregation) */
+  float coords_range;            /* 15.0: the undivided value the blocks receive (egnn_new.py:218) */
+  float edge_cutoff_ligand;
+  float edge_cutoff_pocket;
+  float edge_cutoff_interaction;
+} dsb_config;
+
+typedef struct dsb_dynamics dsb_dynamics; /* opaque: packed weights for one EGNNDynamics module */
+
+/* ---- parameter table: the reference state-dict entries, in the order dsb_dynamics_create wants them.
+ * Names are the reference's state_dict keys ("egnn.e_block_0.gcl_0.edge_mlp.0.weight", ...;
+ * egnn_new.py:15-29, :78-92, :212-222; dynamics.py:27-53).  cross_product_mlp.4.weight is NOT listed:
+ * it aliases coord_mlp.4.weight (egnn_new.py:78, :85, :91). */
+int dsb_param_count(const dsb_config* cfg);
+/* writes the NUL-terminated key of parameter i into buf; returns its element count, or <0. */
+int64_t dsb_param_name(const dsb_config* cfg, int i, char* buf, size_t buflen);
+
+/* ---- module lifetime.  `params[i]` is a device pointer to parameter i (fp32, contiguous, the
+ * reference's own [out,in] layout).  The library copies/re-packs them into its own device buffer
+ * (k-major GEMM operands, factorised first layers) — the caller's tensors are not referenced after
+ * the call returns.  Replaces: EGNNDynamics.__init__ + load_state_dict (dynamics.py:11-85). */
+int dsb_dynamics_create(const dsb_config* cfg, const float* const* params, int n_params,
+                        dsb_dynamics** out);
+void dsb_dynamics_destroy(dsb_dynamics* dyn);
+
+/* Upper bound of directed edges incl. self loops for a batch: sum_g (n_lig_g + n_pocket_g)^2.
+ * Host helper (host pointers). */
+int64_t dsb_edge_capacity(const int64_t* n_lig_per_graph, const int64_t* n_pocket_per_graph,
+                          int n_graphs);
+
+/* Scratch the forward needs (activations, CSR edge list).  The caller owns the buffer (so that a
+ * caching allocator / CUDA graph pool can provide it); contents need not be preserved between calls. */
+size_t dsb_dynamics_workspace_bytes(const dsb_dynamics* dyn, int64_t n_atoms, int64_t n_residues,
+                                    int64_t n_graphs, int64_t edge_capacity);
+
+/* ---- the hot path.  Replaces EGNNDynamics.forward (dynamics.py:87-167), eval mode:
+ *   xh_atoms    [n_atoms, 3+atom_nf]      xh_residues [n_residues, 3+residue_nf]   (row-major fp32)
+ *   t           [t_numel]; t_numel == n_graphs (one per graph) or 1 (shared, dynamics.py:105-107)
+ *   mask_atoms  [n_atoms] int64, mask_residues [n_residues] int64: non-decreasing graph ids in
+ *               [0, n_graphs) (utils.py:146-154)
+ *   out_atoms   [n_atoms, 3+atom_nf]      out_residues [n_residues, 3+residue_nf]
+ *   status      device int32[4]: [0] |= 1 if a NaN reached the coordinate output (the reference raises
+ *               ValueError("NaN detected in EGNN output"), dynamics.py:155-159 — the host wrapper
+ *               turns the flag into that exception); [1] = number of edges of this call;
+ *               [2] |= 1 if the edge list would not fit edge_capacity (outputs invalid). Sticky: the
+ *               library only ORs into [0] and [2], the caller clears them.
+ * Inputs are not modified.  Asynchronous on `stream` (a cudaStream_t passed as void*). */
+int dsb_dynamics_forward(dsb_dynamics* dyn,
+                         const float* xh_atoms, const float* xh_residues,
+                         const float* t, int64_t t_numel,
+                         const int64_t* mask_atoms, const int64_t* mask_residues,
+                         int64_t n_atoms, int64_t n_residues, int64_t n_graphs,
+                         int64_t edge_capacity,
+                         float* out_atoms, float* out_residues,
+                         void* workspace, size_t workspace_bytes,
+                         int32_t* status, void* stream);
+
+/* ---- edge list only.  Replaces EGNNDynamics.get_edges (dynamics.py:169-187): same-graph pairs within
+ * the per-block cut-offs, self loops kept, sorted by (row, col).  rows/cols: device int32[edge_capacity];
+ * n_edges: device int32[1].  Uses `workspace` (same size contract as forward). */
+int dsb_dynamics_edges(dsb_dynamics* dyn,
+                       const float* xh_atoms, const float* xh_residues,
+                       const int64_t* mask_atoms, const int64_t* mask_residues,
+                       int64_t n_atoms, int64_t n_residues, int64_t n_graphs,
+                       int64_t edge_capacity,
+                       int32_t* rows, int32_t* cols, int32_t* n_edges,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernel launches (incl. memsets) the last dsb_dynamics_forward on this module enqueued. */
+int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
+
+/* ---- fused DDPM ligand update (one launch). Replaces the element-wise tail of
+ * ConditionalDDPM.sample_p_zs_given_zt (conditional_model.py:451-460) + sample_normal_zero_com
+ * (:140-160) + remove_mean_batch (:688-696):
+ *   mu   = z/alpha_ts[g] - coef1[g] * eps_hat
+ *   z'   = mu + sigma[g] * noise ;   com_g = mean over ligand atoms of graph g of z'[:, :3]
+ *   z_out[:, :3] = z'[:, :3] - com_g ; z_out[:, 3:] = z'[:, 3:]
+ *   pocket_out[:, :3] = pocket[:, :3] - com_g ; pocket_out[:, 3:] = pocket[:, 3:]
+ * coef: device fp32 [n_graphs, 3] = (alpha_ts, sigma2_ts/alpha_ts/sigma_t, sigma) per graph (z is DIVIDED by
+ * alpha_ts, exactly as conditional_model.py:451 does).
+ * In-place allowed (z_out == z, pocket_out == pocket). */
+int dsb_ddpm_ligand_update(const float* z_lig, const float* eps_hat, const float* noise,
+                           const float* coef, const int64_t* mask_atoms, const int64_t* mask_residues,
+                           const float* xh_pocket, int64_t n_atoms, int64_t n_residues,
+                           int64_t n_graphs, int32_t atom_nf, int32_t residue_nf,
+                           float* z_out, float* xh_pocket_out, void* stream);
+
+const char* dsb_last_error(void);
+const char* dsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSBDD_B200_H_ */

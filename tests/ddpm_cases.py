@@ -1,0 +1,57 @@
+"""Shared definitions of the DDPM-wrapper parity cases (used by the golden generator and the tests)."""
+import torch
+import torch.nn as nn
+
+from diffsbdd_b200.config import DynamicsConfig
+from diffsbdd_b200 import synthetic as syn
+from oracle import egnn_oracle
+
+# small conditional denoiser (kernel-supported dims: H=64) so CPU loops stay fast
+DDPM_CFG = DynamicsConfig(joint_nf=16, hidden_nf=64, n_layers=2)
+HIST = [[0.0, 1.0, 2.0], [1.0, 3.0, 1.0], [2.0, 1.0, 0.5]]
+N_POCKET = [22, 17]
+
+SAMPLER_CASES = {
+    'sample_T6': dict(kind='sample', T=6, timesteps=None, frames=1, n_lig=[7, 5], seed=101),
+    'sample_T12_frames3_sub6': dict(kind='sample', T=12, timesteps=6, frames=3, n_lig=[4, 9], seed=102),
+    'inpaint_T4_r2_ligand': dict(kind='inpaint', T=8, timesteps=4, resamplings=2, n_lig=[8, 6], n_fixed=3,
+                                 center='ligand', seed=103),
+    'inpaint_T3_r1_pocket': dict(kind='inpaint', T=3, timesteps=None, resamplings=1, n_lig=[5, 7], n_fixed=2,
+                                 center='pocket', seed=104),
+    'diversify_3of10': dict(kind='diversify', T=10, noising_steps=3, n_lig=[6, 6], seed=105),
+}
+
+
+class OracleDynamics(nn.Module):
+    """CPU denoiser stand-in with the EGNNDynamics call contract (dynamics.py:87)."""
+
+    def __init__(self, cfg, sd):
+        super().__init__()
+        self.cfg, self.sd = cfg, sd
+        self.update_pocket_coords = cfg.update_pocket_coords
+        self.n_dims = 3
+
+    def forward(self, xh_atoms, xh_residues, t, mask_atoms, mask_residues):
+        return egnn_oracle.denoiser_forward(self.cfg, self.sd, xh_atoms, xh_residues, t, mask_atoms, mask_residues)
+
+
+def make_pocket(device='cpu'):
+    p = syn.synthetic_pocket(DDPM_CFG, N_POCKET, seed=31, spread=3.0)
+    return {k: v.to(device) for k, v in p.items()}
+
+
+def make_ligand(n_lig, n_fixed, device='cpu'):
+    """Reference ``ligand`` dict + 0/1 ``lig_fixed`` (inpaint.py:117-141: first n_fixed atoms of every sample)."""
+    g = torch.Generator().manual_seed(77)
+    n = sum(n_lig)
+    mask = torch.repeat_interleave(torch.arange(len(n_lig)), torch.tensor(n_lig))
+    x = torch.randn((n, 3), generator=g) * 1.5
+    types = torch.randint(0, DDPM_CFG.atom_nf, (n,), generator=g)
+    fixed = torch.zeros(n)
+    start = 0
+    for k in n_lig:
+        fixed[start:start + n_fixed] = 1
+        start += k
+    lig = {'x': x.to(device), 'one_hot': torch.nn.functional.one_hot(types, DDPM_CFG.atom_nf).float().to(device),
+           'size': torch.tensor(n_lig, device=device), 'mask': mask.to(device)}
+    return lig, fixed.to(device)
