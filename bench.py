@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffSBDD denoising hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+metric : ligand atoms/s through the full 500-step DDPM sampling loop (501 denoiser calls), batch of 64
+         synthetic pocket+ligand graphs per GPU (N_L=25, N_P=175 -> N=200), crossdock_fullatom_cond dims.
+step   : ONE complete ``ConditionalDDPM.sample_given_pocket`` of the per-GPU batch.
+value  : whole-job atoms/s with the pocket already resident in HBM (CUDA events, max over ranks).
+e2e    : same metric through the public API (``LigandPocketDDPM.generate_ligand_tensors``) from pinned
+         HOST buffers, host->device copy of the pocket and device->host read of the ligands inside the timed
+         region.
+--impl reference : the reference's CPU implementation of the path (oracle port — /root/reference cannot travel
+         to the GPU box), all host threads, bounded sample per step, extrapolated linearly to 501 calls.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'ligand_atoms_per_sec_500step_ddpm'
+UNIT = 'ligand atoms/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='pockets per GPU')
+    ap.add_argument('--n-lig', type=int, default=25)
+    ap.add_argument('--n-pocket', type=int, default=175)
+    ap.add_argument('--timesteps', type=int, default=500)
+    ap.add_argument('--workload', default='fullatom', choices=['fullatom', 'ca'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--profile-calls', type=int, default=10)
+    ap.add_argument('--cpu-sample-seconds', type=float, default=20.0)
+    return ap.parse_args()
+
+
+def workload(args):
+    from diffsbdd_b200.config import FULLATOM_COND, CA_COND
+    if args.workload == 'fullatom':
+        return FULLATOM_COND, 0.045, (1, 4), 'crossdock_fullatom_cond'
+    return CA_COND, 0.007, (1, 1), 'crossdock_ca_cond'
+
+
+def workload_name(args, yml):
+    return (f'BASELINE configs[2]: conditional {args.workload} model ({yml}.yml dims), {args.timesteps}-step DDPM, '
+            f'batch {args.batch}/GPU, N_L={args.n_lig}, N_P={args.n_pocket}')
+
+
+def hparams(cfg, args, norm_values):
+    egnn = Namespace(device='cuda', joint_nf=cfg.joint_nf, hidden_nf=cfg.hidden_nf, n_layers=cfg.n_layers,
+                     attention=cfg.attention, tanh=cfg.tanh, norm_constant=cfg.norm_constant,
+                     inv_sublayers=cfg.inv_sublayers, sin_embedding=cfg.sin_embedding,
+                     normalization_factor=cfg.normalization_factor, aggregation_method=cfg.aggregation_method,
+                     edge_cutoff_ligand=cfg.edge_cutoff_ligand, edge_cutoff_pocket=cfg.edge_cutoff_pocket,
+                     edge_cutoff_interaction=cfg.edge_cutoff_interaction,
+                     reflection_equivariant=cfg.reflection_equivariant, edge_embedding_dim=cfg.edge_embedding_dim)
+    diff = Namespace(diffusion_steps=args.timesteps, diffusion_noise_schedule='polynomial_2',
+                     diffusion_noise_precision=5.0e-4, diffusion_loss_type='l2', normalize_factors=list(norm_values))
+    hist = np.ones((args.n_lig + 2, args.n_pocket + 2)).tolist()
+    return dict(outdir=None, dataset='crossdock', datadir=None, batch_size=args.batch, lr=1e-3, egnn_params=egnn,
+                diffusion_params=diff, num_workers=0, augment_noise=0, augment_rotation=False, clip_grad=True,
+                eval_epochs=1, eval_params=Namespace(), visualize_sample_epoch=1, visualize_chain_epoch=1,
+                auxiliary_loss=False, loss_params=Namespace(), mode='pocket_conditioning', node_histogram=hist,
+                pocket_representation='full-atom' if args.workload == 'fullatom' else 'CA')
+
+
+# ---- clocks sampler (B200_PROFILING.md "clocks DURING the timed region") -------------------------------------
+class ClockSampler:
+    FIELDS = ('uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.uuid = None
+        try:
+            self.uuid = str(torch.cuda.get_device_properties(device).uuid)
+        except Exception:
+            pass
+        self.rows, self.proc, self.thread = [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            if self.uuid and self.uuid.replace('GPU-', '') not in f[0]:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        load = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
+        return {'sm_mhz': statistics.median(load) if load else None, 'sm_max_mhz': smax,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def l2_flush(buf):
+    buf.add_(1.0)    # read+write 256 MiB > 126 MB L2
+
+
+# ---- CPU baseline: oracle port of the reference's PyTorch path on the host cores -------------------------------
+def cpu_reference_sample(args, budget_s, rank_seed=0, sub_batch=8):
+    """Times the CPU port on a BOUNDED sample of the same workload: the first ``sub_batch`` pockets of the batch
+    (CPU cost is linear in the number of pockets: graphs are independent), 1 reverse step + the final p(x|z0) call
+    repeated until ~budget_s; atoms/s extrapolated to the full 501-call loop (every reverse step has the same cost).
+    The torch thread count is calibrated first (all host cores are offered; the fastest setting is used)."""
+    from diffsbdd_b200 import synthetic as syn
+    from diffsbdd_b200.conditional_model import ConditionalDDPM
+    from oracle.cpu_denoiser import OracleDynamics
+    cfg, density, norm_values, yml = workload(args)
+    cores = os.cpu_count() or 1
+    sd = syn.synthetic_state_dict(cfg, 0)
+    dyn = OracleDynamics(cfg, sd)
+    hist = np.ones((args.n_lig + 2, args.n_pocket + 2)).tolist()
+    ddpm = ConditionalDDPM(dynamics=dyn, atom_nf=cfg.atom_nf, residue_nf=cfg.residue_nf, n_dims=3,
+                           timesteps=args.timesteps, noise_schedule='polynomial_2', noise_precision=5e-4,
+                           loss_type='l2', norm_values=norm_values, size_histogram=hist)
+    ddpm.eval()
+    nb = min(sub_batch, args.batch)
+    pocket = syn.synthetic_pocket(cfg, [args.n_pocket] * nb, seed=3 + rank_seed, density=density)
+    n_lig = torch.full((nb,), args.n_lig, dtype=torch.int64)
+    torch.manual_seed(0)
+
+    def one_sample():
+        t0 = time.perf_counter()
+        ddpm.sample_given_pocket(dict(pocket), n_lig, timesteps=1)      # 2 denoiser calls
+        return time.perf_counter() - t0
+
+    best_threads, best_t = cores, None
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    t_cal0 = time.perf_counter()
+    for th in cands:
+        torch.set_num_threads(th)
+        one_sample()
+        t = one_sample()
+        if best_t is None or t < best_t:
+            best_threads, best_t = th, t
+        if time.perf_counter() - t_cal0 > budget_s:
+            break
+    torch.set_num_threads(best_threads)
+    dyn.calls = 0
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 1 or (time.perf_counter() - t0 < 0.5 * budget_s and reps < 50):
+        one_sample()
+        reps += 1
+    dt = time.perf_counter() - t0
+    per_call = dt / dyn.calls
+    full = per_call * (args.timesteps + 1)
+    atoms = nb * args.n_lig
+    return {'value': atoms / full, 'unit': UNIT, 'cores': best_threads, 'kind': 'port',
+            'sample': (f'oracle port of the reference PyTorch path (oracle/egnn_oracle.py + eager reference-order DDPM '
+                       f'loop) on the first {nb} of the {args.batch} pockets, {dyn.calls} denoiser calls in {dt:.1f} s = '
+                       f'{per_call:.2f} s/call, extrapolated x{args.timesteps + 1} calls; torch threads calibrated over '
+                       f'{cands} of {cores} host cores -> {best_threads}'),
+            'seconds_per_denoiser_call': per_call, 'host_cores': cores, 'torch_threads': best_threads}, dt, dyn.calls
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    _, _, _, yml = workload(args)
+    times = []
+    base = None
+    per_step_budget = max(4.0, min(args.cpu_sample_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        base, dt, calls = cpu_reference_sample(args, per_step_budget)
+        if i >= args.warmup:
+            times.append(dt)
+        if i == 0 and args.warmup + args.steps > 1 and dt * (args.warmup + args.steps) > 240:
+            per_step_budget = max(2.0, per_step_budget / 2)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * statistics.mean(times),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args, yml), 'step': 'bounded sample: ' + base['sample']},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---- B200 arm ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from diffsbdd_b200 import synthetic as syn
+    from diffsbdd_b200.lightning_modules import LigandPocketDDPM
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device (no CPU fallback exists)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    cfg, density, norm_values, yml = workload(args)
+    model = LigandPocketDDPM(**hparams(cfg, args, norm_values))
+    model.ddpm.dynamics.load_state_dict(syn.synthetic_state_dict(cfg, 0))
+    model.to(device).eval()
+    ddpm, dyn = model.ddpm, model.ddpm.dynamics
+    B, NL, NP, T = args.batch, args.n_lig, args.n_pocket, args.timesteps
+
+    pocket_host = syn.synthetic_pocket(cfg, [NP] * B, seed=3 + rank, density=density)
+    pocket_host = {k: v.pin_memory() for k, v in pocket_host.items()}
+    pocket_dev = {k: v.to(device) for k, v in pocket_host.items()}
+    n_lig_host = torch.full((B,), NL, dtype=torch.int64).pin_memory()
+    n_lig_dev = n_lig_host.to(device)
+    flush_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    torch.manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(device)
+
+    gathered = [None]
+
+    def step_device():
+        xh_lig, _, lig_mask, _ = ddpm.sample_given_pocket(dict(pocket_dev), n_lig_dev, timesteps=T)
+        if world > 1:   # the only collective of the path — final gather of the ligands
+            outs = [torch.empty_like(xh_lig) for _ in range(world)]
+            dist.all_gather(outs, xh_lig.contiguous())
+            gathered[0] = outs
+        return xh_lig
+
+    def step_e2e():
+        pocket = {k: v.to(device, non_blocking=True) for k, v in pocket_host.items()}
+        n_lig = n_lig_host.to(device, non_blocking=True)
+        xh_lig, _, lig_mask, _ = model.generate_ligand_tensors(pocket, n_lig, timesteps=T)
+        return xh_lig.cpu(), lig_mask.cpu()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            l2_flush(flush_buf)
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(device)
+    sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    e_last = dyn.last_num_edges
+    atoms_per_step = B * NL * world
+    value = atoms_per_step * args.steps / (ms_total / 1e3)
+
+    # e2e through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in pocket_host.values()) + n_lig_host.numel() * 8
+        d2h = B * NL * (3 + cfg.atom_nf) * 4 + B * NL * 8
+        e2e = {'value': atoms_per_step * args.steps / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
+               'api': 'LigandPocketDDPM.generate_ligand_tensors(pocket[pinned host]->device, ...) -> .cpu()'}
+
+    launches_fwd = dyn.launches_per_forward
+    gpu_launches = args.steps * ((T + 1) * launches_fwd + T)     # + one fused DDPM update kernel per reverse step
+
+    # ---- live kernel timing for the roofline: eager forwards with CUDA events on the launch stream ------------
+    roof = roof32 = kernel_ms = None
+    if rank == 0:
+        st = next(iter(ddpm._graph_cache.values())) if ddpm._graph_cache else None
+        z = st['z'].clone() if st else None
+        pk = st['pocket'].clone() if st else None
+        if z is not None:
+            t_in = torch.full((B, 1), 0.5, device=device)
+            lm, pm = st['lig_mask'], st['pocket_mask']
+            with torch.no_grad():
+                dyn(z, pk, t_in, lm, pm)
+                dyn.set_profiling(True)
+                dyn.collect_profile(reset=True)
+                for _ in range(args.profile_calls):
+                    l2_flush(flush_buf)
+                    dyn(z, pk, t_in, lm, pm)
+                prof = dyn.collect_profile(reset=True)
+                dyn.set_profiling(False)
+            E = dyn.last_num_edges
+            N, H, L, S = B * (NL + NP), cfg.hidden_nf, cfg.n_layers, cfg.inv_sublayers
+            n_gcl = args.profile_calls * L * S
+            gcl_ms = prof['edge_gcl']['ms'] / max(1, n_gcl)
+            alg_bytes = N * 2 * H * 4 + N * H * 4 + E * 12 + N * 16 + (H * H + 7 * H) * 4
+            alg_flops = E * (2 * H * H + 12 * H)
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                    peaks = json.load(f)
+            except Exception:
+                pass
+            hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+            peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else '6.65 TB/s (of fallback)'
+            ach = alg_bytes / (gcl_ms * 1e-3) / 1e9
+            traffic, traffic_src = None, None
+            try:   # DRAM bytes per launch from the committed ncu --set full capture (never measured under the profiler here)
+                with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+                    tr = json.load(f).get(f'edge_gcl_kernel<{H}>')
+                if tr:
+                    traffic, traffic_src = tr['dram_bytes_per_launch'], tr['source']
+            except Exception:
+                pass
+            roof = {'bound': 'hbm', 'kernel': f'edge_gcl_kernel<{H}>', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': ach / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                    'algorithmic_bytes_per_launch': alg_bytes,
+                    'avg_launch_ms': gcl_ms, 'edges': E, 'peak_source': peak_src,
+                    'note': 'kernel is FP32-FMA bound by construction at hidden_nf=256 (SURVEY.md §8(d)); see roofline_fp32'}
+            smax = (clocks.get('sm_max_mhz') or 1965.0)
+            fp32_peak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * 2 * smax * 1e6 / 1e12
+            ach32 = alg_flops / (gcl_ms * 1e-3) / 1e12
+            roof32 = {'bound': 'fp32_simt', 'kernel': 'edge_gcl_kernel<256>', 'achieved': ach32, 'peak': fp32_peak,
+                      'unit': 'TFLOP/s', 'frac': ach32 / fp32_peak, 'algorithmic_flops_per_launch': alg_flops,
+                      'peak_source': f'SMs x 128 FMA x 2 x clocks.max.sm ({smax:.0f} MHz), nominal'}
+            tot = sum(v['ms'] for v in prof.values())
+            kernel_ms = {k: round(v['ms'] / args.profile_calls, 4) for k, v in prof.items()}
+            kernel_ms['total_per_call'] = round(tot / args.profile_calls, 4)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base, _, _ = cpu_reference_sample(args, args.cpu_sample_seconds)
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(args, yml), 'global_batch': B * world, 'batch_per_gpu': B,
+                           'n_lig': NL, 'n_pocket': NP, 'timesteps': T, 'denoiser_calls_per_step': T + 1,
+                           'edges_last_call': e_last, 'parallelism': f'dp{world} (independent pockets per rank, '
+                           'final all_gather of ligands)', 'l2': '256 MiB read+write flush before every timed step',
+                           'loop_engine': 'cuda_graph replay of one reverse step' if ddpm._graph_cache else 'eager',
+                           'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py)'},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': gpu_launches,
+                'launches_per_denoiser_call': launches_fwd, 'roofline': roof, 'roofline_fp32': roof32,
+                'kernel_ms_per_denoiser_call': kernel_ms, 'cpu_baseline': cpu_base}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out, file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out))
-    cmd = [nvcc, '-shared', '-Wno-deprecated-gpu-targets', '-o', LIB_PATH] + objs
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Wno-deprecated-gpu-targets', '-o', LIB_PATH] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed: %s\n%s' % (' '.join(cmd), r.stdout))

@@ -132,11 +132,16 @@ class ConditionalDDPM(EnVariationalDiffusion):
         device = z_lig.device
         dyn: EGNNDynamics = self.dynamics
         lib = _native.load()
-        key = (z_lig.shape, xh_pocket.shape, n_samples, timesteps, id(lig_mask), id(pocket_mask), str(device))
+        key = (tuple(z_lig.shape), tuple(xh_pocket.shape), n_samples, timesteps, str(device))
         st = self._graph_cache.get(key)
+        if st is not None and not (torch.equal(st['lig_mask'], lig_mask) and torch.equal(st['pocket_mask'], pocket_mask)):
+            st = None            # same shapes, different graph layout: re-capture
         if st is None:
             self._graph_cache.clear()
             t_table, coef_table = self._schedule_tables(timesteps, timesteps, device)
+            # the captured step owns static copies of the masks, so one capture serves every later batch with the
+            # same layout (generate_ligands builds fresh mask tensors on every call)
+            lig_mask, pocket_mask = lig_mask.clone(), pocket_mask.clone()
             st = dict(
                 z=torch.empty_like(z_lig), pocket=torch.empty_like(xh_pocket), noise=torch.empty_like(z_lig),
                 t=torch.zeros((n_samples, 1), device=device), coef=torch.zeros((n_samples, 3), device=device),

@@ -326,6 +326,7 @@ void dsb_dynamics_destroy(dsb_dynamics* dyn) {
   if (!dyn) return;
   cudaDeviceSynchronize();
   cudaFree(dyn->blob);
+  if (dyn->prof_ev) { for (int i = 0; i < 2 * kMaxProfEvents; ++i) cudaEventDestroy(dyn->prof_ev[i]); delete[] dyn->prof_ev; }
   delete dyn;
 }
 
@@ -387,46 +388,111 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   }
   if (!status || (!out_atoms && n_atoms) || (!out_residues && n_residues)) { set_error("null output/status"); return DSB_ERR_INVALID_ARGUMENT; }
   cudaStream_t s = (cudaStream_t)stream;
-  int launches = 0;
-  dyn->last_launches = 0;
+  int launches = 0, memsets = 0;
+  dyn->last_launches = 0; dyn->last_memsets = 0;
   if (dm.N == 0) return 0;
   const int H = c.hidden_nf;
   const int nm = c.reflection_equivariant ? 1 : 2;
   const size_t hbytes = sizeof(float) * (size_t)dm.N * H;
 
-  if (int e = launch_plan(dyn, dm, ws, mask_atoms, mask_residues, s)) return e; launches += 1;
-  if (int e = launch_prep(dyn, dm, ws, xh_atoms, xh_residues, t, t_numel, mask_atoms, mask_residues, false, s)) return e; launches += 1;
-  if (int e = launch_edges(dyn, dm, ws, status, s)) return e; launches += 3;
+  // optional per-class timing with CUDA events on the launch stream (never during stream capture)
+  bool prof = dyn->prof_enabled != 0;
+  if (prof) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cs);
+    if (cs != cudaStreamCaptureStatusNone) prof = false;
+  }
+  if (prof && dyn->prof_n > 0) {        // drain the previous forward's intervals into the accumulators
+    for (int i = 0; i < dyn->prof_n; ++i) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(dyn->prof_ev[2 * i + 1]) == cudaSuccess &&
+          cudaEventElapsedTime(&ms, dyn->prof_ev[2 * i], dyn->prof_ev[2 * i + 1]) == cudaSuccess) {
+        dyn->prof_ms[dyn->prof_cls[i]] += ms; dyn->prof_cnt[dyn->prof_cls[i]] += 1;
+      }
+    }
+  }
+  if (prof) dyn->prof_n = 0;
+  int cur_cls = -1;
+  auto mark = [&](int cls) {            // closes the open interval and opens one of class `cls` (-1: just close)
+    if (!prof) return;
+    if (cur_cls >= 0) { cudaEventRecord(dyn->prof_ev[2 * dyn->prof_n + 1], s); dyn->prof_cls[dyn->prof_n] = cur_cls; dyn->prof_n++; }
+    cur_cls = -1;
+    if (cls >= 0 && dyn->prof_n < kMaxProfEvents) { cudaEventRecord(dyn->prof_ev[2 * dyn->prof_n], s); cur_cls = cls; }
+  };
+#define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
+
+  mark(KC_SETUP);
+  DSB_TRY(launch_plan(dyn, dm, ws, mask_atoms, mask_residues, s)); launches += 1;
+  DSB_TRY(launch_prep(dyn, dm, ws, xh_atoms, xh_residues, t, t_numel, mask_atoms, mask_residues, false, s)); launches += 1;
+  DSB_TRY(launch_edges(dyn, dm, ws, status, s)); launches += 3;
   const float4* xcur = ws.xbuf[0];
-  if (nm == 2) { if (int e = launch_coord_finish(dyn, dm, ws, xcur, nullptr, false, s)) return e; launches += 1; }
+  if (nm == 2) { mark(KC_COORD_FINISH); DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, nullptr, false, s)); launches += 1; }
 
   for (int l = 0; l < c.n_layers; ++l) {
     for (int sub = 0; sub < c.inv_sublayers; ++sub) {
       const GclW& G = dyn->w.gcl[l][sub];
+      mark(KC_NODE_GEMM);
       GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0};
-      if (int e = launch_node_gemm(g1, s)) return e;
+      DSB_TRY(launch_node_gemm(g1, s));
+      mark(KC_MEMSET);
       DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
-      if (int e = launch_edge_gcl(dyn, dm, ws, G, xcur, s)) return e;
+      mark(KC_EDGE_GCL);
+      DSB_TRY(launch_edge_gcl(dyn, dm, ws, G, xcur, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
+      mark(KC_NODE_GEMM);
       GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1};
-      if (int e = launch_node_gemm(g2, s)) return e;
+      DSB_TRY(launch_node_gemm(g2, s));
       GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0};
-      if (int e = launch_node_gemm(g3, s)) return e;
-      launches += 5;
+      DSB_TRY(launch_node_gemm(g3, s));
+      launches += 4; memsets += 1;
     }
     const EquivW& Q = dyn->w.eq[l];
+    mark(KC_NODE_GEMM);
     GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, nm * 2 * H, Q.b1, nullptr, 0, ws.P, nm * 2 * H, dm.N, nm * 2 * H, 0};
-    if (int e = launch_node_gemm(g4, s)) return e;
+    DSB_TRY(launch_node_gemm(g4, s));
+    mark(KC_MEMSET);
     DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
-    if (int e = launch_edge_coord(dyn, dm, ws, Q, xcur, s)) return e;
+    mark(KC_EDGE_COORD);
+    DSB_TRY(launch_edge_coord(dyn, dm, ws, Q, xcur, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];
-    if (int e = launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s)) return e;
+    mark(KC_COORD_FINISH);
+    DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
     xcur = xnext;
-    launches += 4;
+    launches += 3; memsets += 1;
   }
-  if (int e = launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s)) return e;
+  mark(KC_POST);
+  DSB_TRY(launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s));
+  mark(-1);
+#undef DSB_TRY
   launches += 1 + (c.update_pocket_coords ? 1 : 0);
   dyn->last_launches = launches;
+  dyn->last_memsets = memsets;
+  return 0;
+}
+
+int dsb_dynamics_set_profiling(dsb_dynamics* dyn, int enabled) {
+  if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (enabled && !dyn->prof_ev) {
+    dyn->prof_ev = new cudaEvent_t[2 * kMaxProfEvents];
+    for (int i = 0; i < 2 * kMaxProfEvents; ++i) DSB_CUDA_OK(cudaEventCreate(&dyn->prof_ev[i]));
+  }
+  dyn->prof_enabled = enabled ? 1 : 0;
+  dyn->prof_n = 0;
+  return 0;
+}
+
+int dsb_dynamics_collect_profile(dsb_dynamics* dyn, double* ms_by_class, int64_t* count_by_class, int reset) {
+  if (!dyn || !ms_by_class || !count_by_class) { set_error("null argument"); return DSB_ERR_INVALID_ARGUMENT; }
+  for (int i = 0; i < dyn->prof_n; ++i) {
+    DSB_CUDA_OK(cudaEventSynchronize(dyn->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    DSB_CUDA_OK(cudaEventElapsedTime(&ms, dyn->prof_ev[2 * i], dyn->prof_ev[2 * i + 1]));
+    dyn->prof_ms[dyn->prof_cls[i]] += ms;
+    dyn->prof_cnt[dyn->prof_cls[i]] += 1;
+  }
+  dyn->prof_n = 0;
+  for (int k = 0; k < KC_COUNT; ++k) { ms_by_class[k] = dyn->prof_ms[k]; count_by_class[k] = dyn->prof_cnt[k]; }
+  if (reset) for (int k = 0; k < KC_COUNT; ++k) { dyn->prof_ms[k] = 0; dyn->prof_cnt[k] = 0; }
   return 0;
 }
 

@@ -75,13 +75,28 @@ struct Dims {
 
 }  // namespace dsb
 
+namespace dsb {
+// kernel classes for the optional per-class CUDA-event timing (dsb_dynamics_set_profiling)
+enum KClass { KC_SETUP = 0, KC_NODE_GEMM = 1, KC_MEMSET = 2, KC_EDGE_GCL = 3, KC_EDGE_COORD = 4,
+              KC_COORD_FINISH = 5, KC_POST = 6, KC_COUNT = 7 };
+constexpr int kMaxProfEvents = 512;
+}
+
 struct dsb_dynamics {
   dsb_config cfg;
   dsb::PackedWeights w;
   float* blob = nullptr;
   size_t blob_floats = 0;
   int num_sms = 148;
-  int last_launches = 0;
+  int last_launches = 0;     // kernels only
+  int last_memsets = 0;
+  // profiling
+  int prof_enabled = 0;
+  cudaEvent_t* prof_ev = nullptr;      // [2 * kMaxProfEvents]
+  int prof_cls[dsb::kMaxProfEvents];
+  int prof_n = 0;
+  double prof_ms[dsb::KC_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  long long prof_cnt[dsb::KC_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace dsb {

@@ -249,6 +249,20 @@ class EGNNDynamics(nn.Module):
             return 0
         return int(_native.load().dsb_dynamics_last_launch_count(C.c_void_p(self._handle)))
 
+    PROFILE_CLASSES = ('setup', 'node_gemm', 'memset', 'edge_gcl', 'edge_coord', 'coord_finish', 'post')
+
+    def set_profiling(self, enabled: bool):
+        """Per-kernel-class CUDA-event timing of eager (non-captured) forwards; see include/diffsbdd_b200.h."""
+        if self._handle is None:
+            raise RuntimeError('run one forward first (the native module is created lazily)')
+        _native.check(_native.load().dsb_dynamics_set_profiling(C.c_void_p(self._handle), int(bool(enabled))))
+
+    def collect_profile(self, reset: bool = True):
+        ms = (C.c_double * 7)()
+        cnt = (C.c_int64 * 7)()
+        _native.check(_native.load().dsb_dynamics_collect_profile(C.c_void_p(self._handle), ms, cnt, int(reset)))
+        return {k: {'ms': ms[i], 'intervals': cnt[i]} for i, k in enumerate(self.PROFILE_CLASSES)}
+
     # ---- the hot path ----------------------------------------------------------------------------------
     def _prepare(self, xh_atoms, xh_residues, mask_atoms, mask_residues, n_graphs_hint):
         device = xh_atoms.device

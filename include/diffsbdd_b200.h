@@ -117,8 +117,17 @@ int dsb_dynamics_edges(dsb_dynamics* dyn,
                        int32_t* rows, int32_t* cols, int32_t* n_edges,
                        void* workspace, size_t workspace_bytes, void* stream);
 
-/* Number of kernel launches (incl. memsets) the last dsb_dynamics_forward on this module enqueued. */
+/* Number of kernel launches (memsets excluded) the last dsb_dynamics_forward on this module enqueued. */
 int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
+
+/* ---- measurement hook (bench.py's live roofline).  When enabled, every non-captured forward brackets
+ * its launches with CUDA events on the launch stream, grouped into 7 kernel classes:
+ *   0 setup (plan, encoders+embedding, edge list)  1 node GEMMs  2 memsets  3 edge_gcl_kernel
+ *   4 edge_coord_kernel  5 coord finish/centroid  6 decoders/output.
+ * collect() synchronises the recorded events and returns accumulated milliseconds and interval counts per
+ * class (host arrays of 7); reset != 0 clears the accumulators. */
+int dsb_dynamics_set_profiling(dsb_dynamics* dyn, int enabled);
+int dsb_dynamics_collect_profile(dsb_dynamics* dyn, double* ms_by_class, int64_t* count_by_class, int reset);
 
 /* ---- fused DDPM ligand update (one launch). Replaces the element-wise tail of
  * ConditionalDDPM.sample_p_zs_given_zt (conditional_model.py:451-460) + sample_normal_zero_com

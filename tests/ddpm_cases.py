@@ -1,10 +1,9 @@
 """Shared definitions of the DDPM-wrapper parity cases (used by the golden generator and the tests)."""
 import torch
-import torch.nn as nn
 
 from diffsbdd_b200.config import DynamicsConfig
 from diffsbdd_b200 import synthetic as syn
-from oracle import egnn_oracle
+from oracle.cpu_denoiser import OracleDynamics  # noqa: F401
 
 # small conditional denoiser (kernel-supported dims: H=64) so CPU loops stay fast
 DDPM_CFG = DynamicsConfig(joint_nf=16, hidden_nf=64, n_layers=2)
@@ -20,19 +19,6 @@ SAMPLER_CASES = {
                                  center='pocket', seed=104),
     'diversify_3of10': dict(kind='diversify', T=10, noising_steps=3, n_lig=[6, 6], seed=105),
 }
-
-
-class OracleDynamics(nn.Module):
-    """CPU denoiser stand-in with the EGNNDynamics call contract (dynamics.py:87)."""
-
-    def __init__(self, cfg, sd):
-        super().__init__()
-        self.cfg, self.sd = cfg, sd
-        self.update_pocket_coords = cfg.update_pocket_coords
-        self.n_dims = 3
-
-    def forward(self, xh_atoms, xh_residues, t, mask_atoms, mask_residues):
-        return egnn_oracle.denoiser_forward(self.cfg, self.sd, xh_atoms, xh_residues, t, mask_atoms, mask_residues)
 
 
 def make_pocket(device='cpu'):
