@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_NAME = 'libdiffsbdd_b200.so'
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ['dsb_api.cu', 'dsb_node.cu', 'dsb_edge.cu']
-HEADERS = [os.path.join(CSRC, 'dsb_internal.cuh'), os.path.join(HERE, '..', 'include', 'diffsbdd_b200.h')]
+SOURCES = ['dsb_api.cu', 'dsb_node.cu', 'dsb_edge.cu', 'dsb_tc.cu']
+HEADERS = [os.path.join(CSRC, 'dsb_internal.cuh'), os.path.join(CSRC, 'dsb_tc.cuh'), os.path.join(HERE, '..', 'include', 'diffsbdd_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets']
 

@@ -99,6 +99,14 @@ struct Packer {
     if (!dry) { int64_t tot = (int64_t)N * K; pack_T_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(dst, ldd, dcol, src, lds, scol, N, K); }
     return dst;
   }
+  // tensor-core B images: allocate [Nn/256][K/32][8192] floats for hi and lo
+  void image_alloc(int Nn, int K, const float** hi, const float** lo, float** hi_w, float** lo_w) {
+    const size_t n = (size_t)(Nn / 256) * (K / 32) * 8192;
+    *hi_w = alloc(n); *lo_w = alloc(n); *hi = *hi_w; *lo = *lo_w;
+  }
+  void image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K) {
+    if (!dry) launch_pack_b_image(hi, lo, src, lds, scol, n_rows, n_dst_off, K);
+  }
   const float* copy(const float* src, int64_t n) {
     float* d = alloc(n);
     if (!dry) pack_copy_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d, src, n);
@@ -166,6 +174,19 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
       G.b3 = cp(g + ".node_mlp.0.bias");
       { float* t = pk.alloc((size_t)H * H); G.W4 = pk.T(P(g + ".node_mlp.2.weight"), H, 0, H, H, t, H, 0); }
       G.b4 = cp(g + ".node_mlp.2.bias");
+      G.W1ab_hi = G.W1ab_lo = G.W2_hi = G.W2_lo = G.W3_hi = G.W3_lo = G.W4_hi = G.W4_lo = nullptr;
+      if (H == 256) {
+        float *hi, *lo;
+        pk.image_alloc(2 * H, H, &G.W1ab_hi, &G.W1ab_lo, &hi, &lo);
+        pk.image(hi, lo, P(g + ".edge_mlp.0.weight"), ld1, 0, H, 0, H);        // receiver part -> columns 0..H-1
+        pk.image(hi, lo, P(g + ".edge_mlp.0.weight"), ld1, H, H, H, H);        // sender part   -> columns H..2H-1
+        pk.image_alloc(H, H, &G.W2_hi, &G.W2_lo, &hi, &lo);
+        pk.image(hi, lo, P(g + ".edge_mlp.2.weight"), H, 0, H, 0, H);
+        pk.image_alloc(H, 2 * H, &G.W3_hi, &G.W3_lo, &hi, &lo);
+        pk.image(hi, lo, P(g + ".node_mlp.0.weight"), 2 * H, 0, H, 0, 2 * H);
+        pk.image_alloc(H, H, &G.W4_hi, &G.W4_lo, &hi, &lo);
+        pk.image(hi, lo, P(g + ".node_mlp.2.weight"), H, 0, H, 0, H);
+      }
     }
     const std::string q = b + ".gcl_equiv";
     EquivW& Q = w.eq[k];
@@ -184,6 +205,19 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     }
     Q.W1 = W1; Q.b1 = b1;
     Q.w3 = cp(q + ".coord_mlp.4.weight");
+    Q.W1_hi = Q.W1_lo = nullptr;
+    for (int m = 0; m < 2; ++m) Q.W2_hi[m] = Q.W2_lo[m] = nullptr;
+    if (H == 256) {
+      float *hi, *lo;
+      pk.image_alloc(nm * 2 * H, H, &Q.W1_hi, &Q.W1_lo, &hi, &lo);
+      for (int m = 0; m < nm; ++m) {
+        pk.image(hi, lo, P(q + names[m] + ".0.weight"), ld1, 0, H, m * 2 * H, H);
+        pk.image(hi, lo, P(q + names[m] + ".0.weight"), ld1, H, H, m * 2 * H + H, H);
+        float *h2, *l2;
+        pk.image_alloc(H, H, &Q.W2_hi[m], &Q.W2_lo[m], &h2, &l2);
+        pk.image(h2, l2, P(q + names[m] + ".2.weight"), H, 0, H, 0, H);
+      }
+    }
   }
   *floats_out = pk.used;
   return 0;
@@ -318,6 +352,7 @@ int dsb_dynamics_create(const dsb_config* cfg, const float* const* params, int n
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (int e = configure_edge_kernels(cfg->hidden_nf)) { cudaFree(d->blob); delete d; return e; }
+  if (cfg->hidden_nf == 256) { if (int e = configure_tc_kernels()) { cudaFree(d->blob); delete d; return e; } }
   *out = d;
   return 0;
 }
@@ -420,6 +455,10 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     if (cls >= 0 && dyn->prof_n < kMaxProfEvents) { cudaEventRecord(dyn->prof_ev[2 * dyn->prof_n], s); cur_cls = cls; }
   };
 #define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
+  const int mm = (H == 256) ? dyn->math_mode : 0;
+  auto gemm = [&](const GemmArgs& ga, const float* bhi, const float* blo) -> int {
+    return ((mm & 1) && bhi) ? launch_tc_node_gemm(dyn, ga, bhi, blo, s) : launch_node_gemm(ga, s);
+  };
 
   mark(KC_SETUP);
   DSB_TRY(launch_plan(dyn, dm, ws, mask_atoms, mask_residues, s)); launches += 1;
@@ -433,27 +472,27 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       const GclW& G = dyn->w.gcl[l][sub];
       mark(KC_NODE_GEMM);
       GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0};
-      DSB_TRY(launch_node_gemm(g1, s));
+      DSB_TRY(gemm(g1, G.W1ab_hi, G.W1ab_lo));
       mark(KC_MEMSET);
       DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
       mark(KC_EDGE_GCL);
-      DSB_TRY(launch_edge_gcl(dyn, dm, ws, G, xcur, s));
+      DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
       GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1};
-      DSB_TRY(launch_node_gemm(g2, s));
+      DSB_TRY(gemm(g2, G.W3_hi, G.W3_lo));
       GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0};
-      DSB_TRY(launch_node_gemm(g3, s));
+      DSB_TRY(gemm(g3, G.W4_hi, G.W4_lo));
       launches += 4; memsets += 1;
     }
     const EquivW& Q = dyn->w.eq[l];
     mark(KC_NODE_GEMM);
     GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, nm * 2 * H, Q.b1, nullptr, 0, ws.P, nm * 2 * H, dm.N, nm * 2 * H, 0};
-    DSB_TRY(launch_node_gemm(g4, s));
+    DSB_TRY(gemm(g4, Q.W1_hi, Q.W1_lo));
     mark(KC_MEMSET);
     DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
     mark(KC_EDGE_COORD);
-    DSB_TRY(launch_edge_coord(dyn, dm, ws, Q, xcur, s));
+    DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];
     mark(KC_COORD_FINISH);
     DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
@@ -467,6 +506,14 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   launches += 1 + (c.update_pocket_coords ? 1 : 0);
   dyn->last_launches = launches;
   dyn->last_memsets = memsets;
+  return 0;
+}
+
+int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {
+  if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (mode < 0 || mode > 7) { set_error("math mode must be a bitmask in [0,7]"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (mode != 0 && dyn->cfg.hidden_nf != 256) { set_error("the tcgen05 3xTF32 path is built for hidden_nf=256 only"); return DSB_ERR_UNSUPPORTED_CONFIG; }
+  dyn->math_mode = mode;
   return 0;
 }
 

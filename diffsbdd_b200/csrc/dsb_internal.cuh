@@ -27,6 +27,11 @@ struct GclW {            // one GCL (reference egnn_new.py:6-66)
   const float* b3;       // [H]
   const float* W4;       // [H][H]   node_mlp.2.weight^T
   const float* b4;       // [H]
+  // tensor-core operand images (H == 256 only; nullptr otherwise): hi/lo TF32 split of B[n][k], [n_tile][k_chunk][256x128B swizzled]
+  const float *W1ab_hi, *W1ab_lo;   // Nn = 2H, K = H
+  const float *W2_hi, *W2_lo;       // Nn = H,  K = H
+  const float *W3_hi, *W3_lo;       // Nn = H,  K = 2H
+  const float *W4_hi, *W4_lo;       // Nn = H,  K = H
 };
 
 struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); index 0 = coord_mlp, 1 = cross_product_mlp
@@ -38,6 +43,8 @@ struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); in
   const float* W2[2];    // [H][H]
   const float* b2[2];    // [H]
   const float* w3;       // [H] shared bias-free last layer (egnn_new.py:78)
+  const float *W1_hi, *W1_lo;       // tensor-core images, Nn = nm*2H, K = H
+  const float *W2_hi[2], *W2_lo[2]; // Nn = H, K = H
 };
 
 struct PackedWeights {
@@ -88,6 +95,7 @@ struct dsb_dynamics {
   float* blob = nullptr;
   size_t blob_floats = 0;
   int num_sms = 148;
+  int math_mode = 0;         // bitmask: 1 node GEMMs, 2 edge_gcl, 4 edge_coord on the tcgen05 3xTF32 path (H == 256)
   int last_launches = 0;     // kernels only
   int last_memsets = 0;
   // profiling
@@ -141,6 +149,13 @@ int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, 
 int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w,
                       const float4* x, cudaStream_t s);
 int configure_edge_kernels(int H);
+
+// ---- tensor-core path (dsb_tc.cu) --------------------------------------------------------------------
+void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K);
+int configure_tc_kernels();
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const float* bhi, const float* blo, cudaStream_t s);
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, cudaStream_t s);
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, cudaStream_t s);
 
 // ---- device math helpers ----------------------------------------------------------------------------
 // SiLU / sigmoid via MUFU.EX2 + MUFU.RCP: relative error ~2 ulp + |x|*6e-8 from the exponent scaling,

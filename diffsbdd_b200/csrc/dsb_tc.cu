@@ -1,0 +1,540 @@
+// Tensor-core (tcgen05 / TMEM) kernels of the denoiser: 3xTF32 split products with fp32 accumulation in TMEM.
+//
+//   tc_node_gemm_kernel — C = act([A1 | A2/div] @ W + bias) (+R)        (node GEMMs: egnn_new.py:21-24, factorised W1a/W1b)
+//   tc_edge_gcl_kernel  — GCL.edge_model + receiver segment sum          (egnn_new.py:31-52)
+//   tc_edge_coord_kernel— EquivariantUpdate.coord_model                  (egnn_new.py:96-116)
+//
+// One persistent CTA per SM, 14 warps, warp-specialised (see dsb_tc.cuh):
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = one tile row), bias/SiLU/gate, segment sums, RED/STG
+//   warps 4-11  producers: build the A operand chunk (gather Pa[row]+Pb[col]+radial terms, SiLU, hi/lo split) straight
+//               into 128B-swizzled shared memory; fence.proxy.async; arrive on full_x
+//   warp 12     MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 split terms) per 32-wide k-chunk
+//   warp 13     TMA issuer: cp.async.bulk of the pre-split, pre-swizzled weight chunk images (hi, lo) -> full_w
+// Two shared-memory stages (96 KB each) and two 256-column TMEM accumulators: the epilogue of tile t overlaps the
+// main loop of tile t+1.
+#include "dsb_tc.cuh"
+
+namespace dsb {
+using namespace tc;
+
+// =====================================================================================================
+// weight images: B[n][k] (= the reference's own [out][in] Linear layout) split into hi/lo and laid out as
+// [n_tile][k_chunk][256 rows x 128 B, SWIZZLE_128B] so that one k-chunk is a single 32 KB bulk copy.
+// =====================================================================================================
+__global__ void pack_b_image_kernel(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src, int lds,
+                                    int scol, int n_rows, int n_dst_off, int K, int chunks) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_rows * K) return;
+  const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K);
+  const int nd = n_dst_off + n, nt = nd / TN, nl = nd % TN;
+  const int kc = k / TKC, c = (k % TKC) >> 2, j = k & 3;
+  const size_t off = ((size_t)nt * chunks + kc) * B_CHUNK_FLOATS + sw128_offset(nl, c) / 4 + j;
+  const float w = src[(size_t)n * lds + scol + k];
+  const float h = tf32_hi(w);
+  hi[off] = h;
+  lo[off] = w - h;
+}
+
+void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K) {
+  const int64_t tot = (int64_t)n_rows * K;
+  pack_b_image_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(hi, lo, src, lds, scol, n_rows, n_dst_off, K, K / TKC);
+}
+
+// ---- common prologue / epilogue of every TC kernel -----------------------------------------------------------------
+constexpr size_t kControlBytes = 128;      // keeps the per-kernel extras 16-byte aligned for float4 access
+static_assert(sizeof(Control) <= kControlBytes, "Control block grew");
+struct Carve {
+  char* stages;
+  Control* ctl;
+  char* extra;
+};
+__device__ __forceinline__ Carve carve_smem(uint8_t* raw) {
+  const uint32_t base = smem_u32(raw);
+  const uint32_t pad = (1024u - (base & 1023u)) & 1023u;
+  Carve c;
+  c.stages = reinterpret_cast<char*>(raw) + pad;
+  c.ctl = reinterpret_cast<Control*>(c.stages + NSTAGE * STAGE_BYTES);
+  c.extra = reinterpret_cast<char*>(c.ctl) + kControlBytes;
+  return c;
+}
+constexpr size_t kTcSmemBase = 1024 + (size_t)NSTAGE * STAGE_BYTES + kControlBytes;
+
+__device__ __forceinline__ void tc_begin(Control* ctl, int warp) {
+  if (threadIdx.x == 0) control_init(ctl);
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+__device__ __forceinline__ void tc_end(Control* ctl, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(ctl->tmem_base, 512);
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory"); }
+
+__device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float* bhi, const float* blo, uint32_t& g, int chunks) {
+  for (int kc = 0; kc < chunks; ++kc, ++g) {
+    const int s = g & 1;
+    mbar_wait(&ctl->empty[s], ((g >> 1) & 1) ^ 1);
+    char* st = stages + (size_t)s * STAGE_BYTES + 2 * A_CHUNK_BYTES;
+    mbar_arrive_expect_tx(&ctl->full_w[s], 2 * B_CHUNK_BYTES);
+    bulk_g2s(st, bhi + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
+    bulk_g2s(st + B_CHUNK_BYTES, blo + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
+  }
+}
+
+// =====================================================================================================
+// node GEMM
+// =====================================================================================================
+struct TcGemmArgs {
+  const float* A1; int lda1; int K1;
+  const float* A2; int lda2; int K2; float div2;
+  const float* Bhi; const float* Blo;        // [Nn/256][K/32][8192]
+  const float* bias; const float* R; int ldr;
+  float* C; int ldc; int M; int Nn; int act;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const Carve cv = carve_smem(smem_raw);
+  Control* ctl = cv.ctl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntn = g.Nn / TN, ntm = (g.M + TM - 1) / TM;
+  const int n_tiles = ntn * ntm;
+  const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (n_my == 0) return;
+  const int K = g.K1 + g.K2, chunks = K / TKC;
+  tc_begin(ctl, warp);
+
+  if (warp < EPI_WARPS) {
+    const int r = threadIdx.x;
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int m0 = (tile / ntn) * TM, n0 = (tile % ntn) * TN;
+      const int a = it & 1;
+      mbar_wait(&ctl->acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      const int row = m0 + r;
+      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * TN);
+#pragma unroll 1
+      for (int cb = 0; cb < TN / 32; ++cb) {
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+        if (row < g.M) {
+          const int n = n0 + cb * 32;
+          if (g.bias) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = *reinterpret_cast<const float4*>(g.bias + n + 4 * q);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+          }
+          if (g.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+          if (g.R) {
+            const float* rr = g.R + (size_t)row * g.ldr + n;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 x = *reinterpret_cast<const float4*>(rr + 4 * q);
+              v[4 * q] = x.x + v[4 * q]; v[4 * q + 1] = x.y + v[4 * q + 1]; v[4 * q + 2] = x.z + v[4 * q + 2]; v[4 * q + 3] = x.w + v[4 * q + 3];
+            }
+          }
+          float* cc = g.C + (size_t)row * g.ldc + n;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(cc + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->epi_done[a]);
+    }
+  } else if (warp < MMA_WARP) {
+    const int ptid = threadIdx.x - EPI_WARPS * 32;
+    const int pr = ptid >> 1, phf = ptid & 1;
+    uint32_t gc = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int m = (tile / ntn) * TM + pr;
+      const bool valid = m < g.M;
+      for (int kc = 0; kc < chunks; ++kc, ++gc) {
+        const int s = gc & 1;
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = kc * TKC + (phf + 2 * q) * 4;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) {
+            if (k < g.K1) {
+              x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k);
+            } else {
+              x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1));
+              if (g.div2 != 1.0f) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
+            }
+          }
+          v[q] = x;
+        }
+        mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+        char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, pr, phf + 2 * q, v[q]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) mma_role(ctl, cv.stages, n_my, chunks);
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int nt = tile % ntn;
+        tma_role(ctl, cv.stages, g.Bhi + (size_t)nt * chunks * B_CHUNK_FLOATS, g.Blo + (size_t)nt * chunks * B_CHUNK_FLOATS, gc, chunks);
+      }
+    }
+    __syncwarp();
+  }
+  tc_end(ctl, warp);
+}
+
+// =====================================================================================================
+// edge kernels
+// =====================================================================================================
+constexpr int H256 = 256;
+constexpr int EPI_T_STRIDE = 33;
+
+struct EdgeExtra {            // shared memory after Control
+  float vec[2][3 * H256];     // per MLP: wr, wr0, b2   (the edge-type table tb stays in global/L1)
+  float wa[H256];             // attention weight (GCL) or w3 (coord)
+  float d2[2][TM], d0[2][TM];
+  int row[2][TM], col[2][TM], type[2][TM];
+  float phi[2][TM];           // coord kernel: phi of MLP 0, per tile parity
+  union {
+    float T[EPI_WARPS][32 * EPI_T_STRIDE];                     // GCL: per-warp transpose buffer
+    struct { float dir[2][6][TM]; float T4[EPI_WARPS][32 * 4]; } c;   // coord: directions + small transpose buffer
+  } u;
+};
+
+struct TcEdgeArgs {
+  const float* P; int ldp;
+  const float4* x; const float4* cent; const int32_t* gid;
+  const int32_t* row_ptr; int n_rows;        // edges [0, row_ptr[n_rows])
+  const int32_t *erow, *ecol; const float* ed0; int NL;
+  int nm;                                    // MLPs per tile: 1 (GCL, reflection-equivariant coord) or 2 (coord + cross)
+  const float* W2hi[2]; const float* W2lo[2];   // [8][8192] images
+  const float* wr[2]; const float* wr0[2]; const float* tb[2]; const float* b2[2];
+  const float* wa; const float* ba;          // GCL attention (nullptr: none) / coord: wa = w3
+  float norm_constant, coords_range; int use_tanh;
+  float* agg;                                // GCL: [N][H] raw sums
+  float4* xagg;                              // coord: [N] raw sums of trans
+};
+
+// per-edge scalars of tile `e0`, written by the 128 even producer threads
+template <bool COORD>
+__device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex, int par, int pr, int e0, int E) {
+  const int e = e0 + pr;
+  int r = -1, c = 0, ty = 0; float d2 = 0.f, d0 = 0.f;
+  float dir[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (e < E) {
+    r = a.erow[e]; c = a.ecol[e]; d0 = a.ed0[e];
+    const float4 xi = a.x[r], xj = a.x[c];
+    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    d2 = dx * dx + dy * dy + dz * dz;
+    ty = (r < a.NL) == (c < a.NL) ? (r < a.NL ? 1 : 2) : 0;
+    if (COORD) {
+      const float den = sqrtf(d2 + 1e-8f) + a.norm_constant;            // egnn_new.py:300-301
+      dir[0] = dx / den; dir[1] = dy / den; dir[2] = dz / den;
+      if (a.nm == 2) {                                                   // egnn_new.py:312-315
+        const float4 m = a.cent[a.gid[r]];
+        const float ax = xi.x - m.x, ay = xi.y - m.y, az = xi.z - m.z;
+        const float bx = xj.x - m.x, by = xj.y - m.y, bz = xj.z - m.z;
+        const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        const float cn = sqrtf(cx * cx + cy * cy + cz * cz) + a.norm_constant;
+        dir[3] = cx / cn; dir[4] = cy / cn; dir[5] = cz / cn;
+      }
+    }
+  }
+  ex->row[par][pr] = r; ex->col[par][pr] = c; ex->d2[par][pr] = d2; ex->d0[par][pr] = d0; ex->type[par][pr] = ty;
+  if (COORD) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ex->u.c.dir[par][k][pr] = dir[k];
+  }
+}
+
+// Virtual tile vt = tile * nm + m  (m-th MLP of the tile).  par(tile) selects the scalar buffers, a = vt & 1 the accumulator.
+template <bool COORD>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const Carve cv = carve_smem(smem_raw);
+  Control* ctl = cv.ctl;
+  EdgeExtra* ex = reinterpret_cast<EdgeExtra*>(cv.extra);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int E = a.row_ptr[a.n_rows];
+  const int n_tiles = (E + TM - 1) / TM;
+  const int n_my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (n_my_tiles == 0) return;
+  const int nm = a.nm;
+  const int n_my = n_my_tiles * nm;            // virtual tiles
+  constexpr int chunks = H256 / TKC;
+  const bool has_tb = a.tb[0] != nullptr;
+
+  for (int i = threadIdx.x; i < H256; i += TC_THREADS) {
+    for (int m = 0; m < nm; ++m) {
+      float* v = ex->vec[m];
+      v[i] = a.wr[m][i]; v[H256 + i] = a.wr0[m][i]; v[2 * H256 + i] = a.b2[m][i];
+    }
+    ex->wa[i] = a.wa ? a.wa[i] : 0.f;
+  }
+  tc_begin(ctl, warp);        // contains the __syncthreads that publishes the vectors
+
+  if (warp < EPI_WARPS) {
+    // ------------------------------------------------------------------------------------------ epilogue
+    const bool has_att = (!COORD) && a.wa != nullptr;
+    const float ba = has_att ? a.ba[0] : 0.f;
+    float* T = COORD ? ex->u.c.T4[warp] : ex->u.T[warp];
+    for (int vt = 0; vt < n_my; ++vt) {
+      const int it = vt / nm, m = vt - it * nm;
+      const int par = it & 1, acc = vt & 1;
+      if (m == 0) mbar_wait(&ctl->scal_full[par], (it >> 1) & 1);
+      mbar_wait(&ctl->acc_full[acc], (vt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TN);
+      const float* b2 = ex->vec[m] + 2 * H256;
+      const int myrow = ex->row[par][warp * 32 + lane];
+      // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
+      float s = 0.f;
+#pragma unroll 1
+      for (int cb = 0; cb < TN / 32; ++cb) {
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(b2 + cb * 32 + 4 * q);
+          const float4 ww = *reinterpret_cast<const float4*>(ex->wa + cb * 32 + 4 * q);
+          v[4 * q] = silu_f(v[4 * q] + bb.x); v[4 * q + 1] = silu_f(v[4 * q + 1] + bb.y);
+          v[4 * q + 2] = silu_f(v[4 * q + 2] + bb.z); v[4 * q + 3] = silu_f(v[4 * q + 3] + bb.w);
+          s = fmaf(v[4 * q], ww.x, s); s = fmaf(v[4 * q + 1], ww.y, s); s = fmaf(v[4 * q + 2], ww.z, s); s = fmaf(v[4 * q + 3], ww.w, s);
+        }
+        if (!COORD) tmem_st32(taddr + cb * 32, v);
+      }
+      if (!COORD) {
+        tmem_wait_st();
+        const float gate = has_att ? sigmoid_f(s + ba) : 1.0f;
+        // segment structure of this warp's 32 rows (uniform across the 8 column blocks)
+        const int prev = __shfl_up_sync(0xffffffffu, myrow, 1);
+        const unsigned seg_start = __ballot_sync(0xffffffffu, lane == 0 || myrow != prev);
+        // pass 2: e = m * gate -> transpose through shared memory -> in-order segmented column sums -> RED
+#pragma unroll 1
+        for (int cb = 0; cb < TN / 32; ++cb) {
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) T[lane * EPI_T_STRIDE + j] = v[j] * gate;
+          __syncwarp();
+          float sum = 0.f;
+          float* dst = a.agg + cb * 32 + lane;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr > 0 && ((seg_start >> rr) & 1u)) {
+              const int prow = __shfl_sync(0xffffffffu, myrow, rr - 1);
+              if (prow >= 0) atomicAdd(dst + (size_t)prow * H256, sum);
+              sum = 0.f;
+            }
+            sum += T[rr * EPI_T_STRIDE + lane];
+          }
+          {
+            const int prow = __shfl_sync(0xffffffffu, myrow, 31);
+            if (prow >= 0) atomicAdd(dst + (size_t)prow * H256, sum);
+          }
+          __syncwarp();
+        }
+      } else {
+        // coord: s = phi_m for this edge row
+        const int r = warp * 32 + lane;
+        if (m == 0 && nm == 2) {
+          ex->phi[par][r] = s;
+        } else {
+          const float p0 = (nm == 2) ? ex->phi[par][r] : s;
+          const float p1 = s;
+          float tr[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {     // egnn_new.py:100-109
+            float t = a.use_tanh ? (ex->u.c.dir[par][k][r] * tanhf(p0)) * a.coords_range : ex->u.c.dir[par][k][r] * p0;
+            if (nm == 2) {
+              const float pc = a.use_tanh ? tanhf(p1) * a.coords_range : p1;
+              t = t + ex->u.c.dir[par][3 + k][r] * pc;
+            }
+            tr[k] = myrow >= 0 ? t : 0.f;
+          }
+          // in-order segmented sum over the warp's 32 rows: lanes 0..2 take one component each
+          T[lane * 4 + 0] = tr[0]; T[lane * 4 + 1] = tr[1]; T[lane * 4 + 2] = tr[2];
+          __syncwarp();
+          if (lane < 3) {
+            int cur = -1; float sum = 0.f;
+            float* dst = reinterpret_cast<float*>(a.xagg);
+            for (int rr = 0; rr < 32; ++rr) {
+              const int row = ex->row[par][warp * 32 + rr];
+              if (row != cur) {
+                if (cur >= 0) atomicAdd(dst + (size_t)cur * 4 + lane, sum);
+                cur = row; sum = 0.f;
+              }
+              if (row >= 0) sum += T[rr * 4 + lane];
+            }
+            if (cur >= 0) atomicAdd(dst + (size_t)cur * 4 + lane, sum);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctl->epi_done[acc]);
+        if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]);
+      }
+    }
+  } else if (warp < MMA_WARP) {
+    // ------------------------------------------------------------------------------------------ producers
+    const int ptid = threadIdx.x - EPI_WARPS * 32;
+    const int pr = ptid >> 1, phf = ptid & 1;
+    uint32_t gc = 0;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int par = it & 1;
+      const int e0 = (blockIdx.x + it * gridDim.x) * TM;
+      mbar_wait(&ctl->scal_empty[par], ((it >> 1) & 1) ^ 1);   // epilogue finished the tile that last used these buffers
+      if (phf == 0) edge_scalars<COORD>(a, ex, par, pr, e0, E);
+      producers_sync();
+      if (ptid == 0) mbar_arrive(&ctl->scal_full[par]);
+      const int prow = ex->row[par][pr] < 0 ? 0 : ex->row[par][pr];
+      const int pcol = ex->col[par][pr];
+      const float pd2 = ex->d2[par][pr], pd0 = ex->d0[par][pr];
+      const int ptype = ex->type[par][pr];
+      for (int m = 0; m < nm; ++m) {
+        const float* Pa = a.P + (size_t)prow * a.ldp + m * 2 * H256;
+        const float* Pb = a.P + (size_t)pcol * a.ldp + m * 2 * H256 + H256;
+        const float* wr = ex->vec[m]; const float* wr0 = wr + H256;
+        const float* tb = has_tb ? a.tb[m] + ptype * H256 : nullptr;
+        float4 ga[4], gb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k0 = (phf + 2 * q) * 4;
+          ga[q] = *reinterpret_cast<const float4*>(Pa + k0);
+          gb[q] = *reinterpret_cast<const float4*>(Pb + k0);
+        }
+#pragma unroll 1
+        for (int kc = 0; kc < chunks; ++kc, ++gc) {
+          const int s = gc & 1;
+          float4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k0 = kc * TKC + (phf + 2 * q) * 4;
+            const float4 r4 = *reinterpret_cast<const float4*>(wr + k0);
+            const float4 r04 = *reinterpret_cast<const float4*>(wr0 + k0);
+            float u0 = fmaf(pd0, r04.x, fmaf(pd2, r4.x, ga[q].x + gb[q].x));
+            float u1 = fmaf(pd0, r04.y, fmaf(pd2, r4.y, ga[q].y + gb[q].y));
+            float u2 = fmaf(pd0, r04.z, fmaf(pd2, r4.z, ga[q].z + gb[q].z));
+            float u3 = fmaf(pd0, r04.w, fmaf(pd2, r4.w, ga[q].w + gb[q].w));
+            if (has_tb) {
+              const float4 t4 = *reinterpret_cast<const float4*>(tb + k0);
+              u0 += t4.x; u1 += t4.y; u2 += t4.z; u3 += t4.w;
+            }
+            v[q] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
+          }
+          if (kc + 1 < chunks) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int k0 = (kc + 1) * TKC + (phf + 2 * q) * 4;
+              ga[q] = *reinterpret_cast<const float4*>(Pa + k0);
+              gb[q] = *reinterpret_cast<const float4*>(Pb + k0);
+            }
+          }
+          mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+          char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, pr, phf + 2 * q, v[q]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) mma_role(ctl, cv.stages, n_my, chunks);
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int vt = 0; vt < n_my; ++vt) {
+        const int m = vt % nm;
+        tma_role(ctl, cv.stages, a.W2hi[m], a.W2lo[m], gc, chunks);
+      }
+    }
+    __syncwarp();
+  }
+  tc_end(ctl, warp);
+}
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+static size_t gemm_smem_bytes() { return kTcSmemBase; }
+static size_t edge_smem_bytes() { return kTcSmemBase + sizeof(EdgeExtra); }
+
+int configure_tc_kernels() {
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  return 0;
+}
+
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const float* bhi, const float* blo, cudaStream_t s) {
+  if (g.M == 0) return 0;
+  const int K = g.K1 + g.K2;
+  if ((g.Nn % TN) || (K % TKC) || (g.K1 % TKC) || (g.lda1 % 4) || (g.ldc % 4)) {
+    set_error("tc_node_gemm: unsupported shape K1=%d K2=%d Nn=%d", g.K1, g.K2, g.Nn);
+    return DSB_ERR_INVALID_ARGUMENT;
+  }
+  TcGemmArgs a;
+  a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2;
+  a.Bhi = bhi; a.Blo = blo; a.bias = g.bias; a.R = g.R; a.ldr = g.ldr; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.Nn = g.Nn; a.act = g.act;
+  const int n_tiles = (g.Nn / TN) * ((g.M + TM - 1) / TM);
+  const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
+  tc_node_gemm_kernel<<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, cudaStream_t s) {
+  TcEdgeArgs a = {};
+  a.P = ws.P; a.ldp = 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.N;
+  a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.nm = 1;
+  a.W2hi[0] = w.W2_hi; a.W2lo[0] = w.W2_lo; a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
+  a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg;
+  tc_edge_kernel<false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, cudaStream_t s) {
+  const dsb_config& c = d->cfg;
+  TcEdgeArgs a = {};
+  a.nm = c.reflection_equivariant ? 1 : 2;
+  a.P = ws.P; a.ldp = a.nm * 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
+  a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL;
+  for (int m = 0; m < a.nm; ++m) {
+    a.W2hi[m] = w.W2_hi[m]; a.W2lo[m] = w.W2_lo[m]; a.wr[m] = w.wr[m]; a.wr0[m] = w.wr0[m]; a.tb[m] = w.tb[m]; a.b2[m] = w.b2[m];
+  }
+  a.wa = w.w3; a.ba = nullptr;
+  a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg;
+  tc_edge_kernel<true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dsb

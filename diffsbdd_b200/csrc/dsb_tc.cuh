@@ -1,0 +1,210 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the shared pipeline pieces of the tensor-core path.
+//
+// Numerics: every contraction is a 3xTF32 split product accumulated in fp32 inside TMEM:
+//     a = a_hi + a_lo,  a_hi = cvt.rna.tf32(a),  a_lo = a - a_hi   (exact; the MMA truncates a_lo to 11 bits: 2^-23 |a|)
+//     a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi                       (dropped a_lo.b_lo ~ 2^-24 |a||b|)
+// which keeps fp32-grade accuracy (the parity tolerance is atol 1e-5 / rtol 1e-4; plain TF32 would be ~1e-3).
+//
+// Operand layout (both operands K-major, SWIZZLE_128B, fp32 words): a tile of R rows x 32 k-values is R rows of
+// 128 bytes; 8-row groups are 1024 B apart (SBO); inside a row the 16-byte chunk c sits at position c ^ (row & 7).
+// One tcgen05.mma kind::tf32 consumes K=8 (32 bytes); stepping K inside the swizzled row = advancing the descriptor
+// start address by 32 bytes.
+#pragma once
+#include "dsb_internal.cuh"
+
+namespace dsb {
+namespace tc {
+
+constexpr int TM = 128;            // rows (edges / nodes) per tile = TMEM lanes
+constexpr int TN = 256;            // accumulator columns per tile
+constexpr int TKC = 32;            // k-values per chunk (one 128B swizzle row)
+constexpr int A_CHUNK_BYTES = TM * 128;        // 16 KB
+constexpr int B_CHUNK_BYTES = TN * 128;        // 32 KB
+constexpr int B_CHUNK_FLOATS = TN * TKC;       // 8192
+constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES + 2 * B_CHUNK_BYTES;   // Xhi, Xlo, Whi, Wlo = 96 KB
+constexpr int NSTAGE = 2;
+
+constexpr int EPI_WARPS = 4;       // warps 0..3  (warp w owns TMEM lanes 32w..32w+31)
+constexpr int PROD_WARPS = 8;      // warps 4..11
+constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;        // 12
+constexpr int TMA_WARP = MMA_WARP + 1;                  // 13
+constexpr int TC_THREADS = (TMA_WARP + 1) * 32;         // 448
+constexpr int PROD_THREADS = PROD_WARPS * 32;           // 256
+
+// instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128  (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t IDESC_TF32_M128_N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must trap (CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) { printf("dsb tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- bulk copy global -> shared (UBLKCP), completion on an mbarrier -------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {         // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread i of the warp gets lane (base_lane + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  // the registers are only valid after tcgen05.wait::ld; keep the wait fused here so no use can be scheduled before it
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// ---- UMMA ----------------------------------------------------------------------------------------------------------
+// K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
+// version 1 <<46 | layout SWIZZLE_128B(2) <<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  return __uint_as_float(h);
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a [rows][128 B] SWIZZLE_128B tile
+__device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// producer helper: split 4 consecutive k-values and store them (hi, lo) at (row, chunk) of the stage's A tiles
+__device__ __forceinline__ void store_split(char* a_hi, char* a_lo, int row, int chunk, float4 v) {
+  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  const uint32_t off = sw128_offset(row, chunk);
+  *reinterpret_cast<float4*>(a_hi + off) = h;
+  *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
+// ---- shared-memory control block -------------------------------------------------------------------------------------
+struct Control {
+  uint64_t full_x[NSTAGE];     // producers -> MMA   (count PROD_WARPS)
+  uint64_t full_w[NSTAGE];     // TMA -> MMA         (count 1 + tx bytes)
+  uint64_t empty[NSTAGE];      // MMA commit -> producers, TMA (count 1)
+  uint64_t acc_full[2];        // MMA commit -> epilogue (count 1)
+  uint64_t epi_done[2];        // epilogue -> MMA, producers (count EPI_WARPS)
+  uint64_t scal_full[2];       // producers -> epilogue (count 1): per-edge scalars of the tile are in shared memory
+  uint64_t scal_empty[2];      // epilogue -> producers (count EPI_WARPS): scalar buffers of the tile may be overwritten
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void control_init(Control* c) {
+  for (int s = 0; s < NSTAGE; ++s) { mbar_init(&c->full_x[s], PROD_WARPS); mbar_init(&c->full_w[s], 1); mbar_init(&c->empty[s], 1); }
+  for (int a = 0; a < 2; ++a) { mbar_init(&c->acc_full[a], 1); mbar_init(&c->epi_done[a], EPI_WARPS); mbar_init(&c->scal_full[a], 1); mbar_init(&c->scal_empty[a], EPI_WARPS); }
+  fence_barrier_init();
+}
+
+// ---- MMA issuer (one thread): per tile, per chunk: 4 k-steps x 3 split products ------------------------------------------
+__device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile) {
+  const uint32_t tmem = ctl->tmem_base;
+  uint32_t g = 0;
+  for (int it = 0; it < n_my_tiles; ++it) {
+    const int a = it & 1;
+    mbar_wait(&ctl->epi_done[a], ((it >> 1) & 1) ^ 1);      // accumulator buffer drained by the epilogue
+    tc_fence_after();
+    const uint32_t d = tmem + (uint32_t)(a * TN);
+    for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
+      const int s = g & 1;
+      const uint32_t par = (g >> 1) & 1;
+      mbar_wait(&ctl->full_w[s], par);
+      mbar_wait(&ctl->full_x[s], par);
+      tc_fence_after();
+      char* st = stages + (size_t)s * STAGE_BYTES;
+      const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t ko = ks * 32;
+        umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, (kc | ks) ? 1u : 0u);
+        umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
+        umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
+      }
+      umma_commit(&ctl->empty[s]);          // stage reusable once these MMAs have read it
+    }
+    umma_commit(&ctl->acc_full[a]);         // accumulator complete
+  }
+}
+
+}  // namespace tc
+}  // namespace dsb

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -147,6 +148,9 @@ class EGNNDynamics(nn.Module):
         self._workspace: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
         self.defer_status_check = False    # samplers that CUDA-graph the loop check once at the end
+        # arithmetic path: bitmask 1 node GEMMs | 2 edge kernel | 4 coordinate kernel on tcgen05 (3xTF32, fp32-grade),
+        # 0 = fp32 FFMA kernels.  'auto' = 7 when hidden_nf == 256 (the only width with tensor-core kernels), else 0.
+        self._math_mode = os.environ.get('DSB_MATH_MODE', 'auto')
         self.to(device)
 
     # ---- native handle management ---------------------------------------------------------------------
@@ -164,6 +168,23 @@ class EGNNDynamics(nn.Module):
             coords_range=15.0,   # the blocks receive the undivided value (egnn_new.py:197 vs :218)
             edge_cutoff_ligand=neg(c.edge_cutoff_ligand), edge_cutoff_pocket=neg(c.edge_cutoff_pocket),
             edge_cutoff_interaction=neg(c.edge_cutoff_interaction))
+
+    @property
+    def math_mode(self) -> int:
+        m = self._math_mode
+        if m in ('auto', None):
+            return 7 if self.cfg.hidden_nf == 256 else 0
+        if m == 'fp32':
+            return 0
+        if m == '3xtf32':
+            return 7
+        return int(m)
+
+    @math_mode.setter
+    def math_mode(self, value):
+        self._math_mode = value
+        if self._handle is not None:
+            _native.check(_native.load().dsb_dynamics_set_math_mode(C.c_void_p(self._handle), self.math_mode))
 
     def _params_by_key(self) -> Dict[str, torch.Tensor]:
         return dict(self.named_parameters(remove_duplicate=False))
@@ -210,6 +231,7 @@ class EGNNDynamics(nn.Module):
             torch.cuda.current_stream().synchronize()
             _native.check(lib.dsb_dynamics_create(C.byref(ccfg), ptrs, len(names), C.byref(out)))
         self._handle, self._handle_sig = out.value, sig
+        _native.check(lib.dsb_dynamics_set_math_mode(C.c_void_p(self._handle), self.math_mode))
 
     def _scratch(self, device, n_atoms, n_res, n_graphs, ecap) -> torch.Tensor:
         lib = _native.load()

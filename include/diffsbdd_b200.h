@@ -120,6 +120,12 @@ int dsb_dynamics_edges(dsb_dynamics* dyn,
 /* Number of kernel launches (memsets excluded) the last dsb_dynamics_forward on this module enqueued. */
 int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
 
+/* ---- arithmetic path.  mode is a bitmask: 1 = node GEMMs, 2 = edge (GCL) kernel, 4 = coordinate edge kernel run on
+ * the tensor pipe (tcgen05.mma kind::tf32, 3xTF32 split products hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM:
+ * fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance); 0 = fp32 FFMA kernels everywhere.
+ * Only hidden_nf == 256 has tensor-core kernels; other widths must use 0. */
+int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode);
+
 /* ---- measurement hook (bench.py's live roofline).  When enabled, every non-captured forward brackets
  * its launches with CUDA events on the launch stream, grouped into 7 kernel classes:
  *   0 setup (plan, encoders+embedding, edge list)  1 node GEMMs  2 memsets  3 edge_gcl_kernel
