@@ -1,5 +1,6 @@
 // C ABI of libdiffsbdd_b200.so: parameter table, weight packing, workspace carve-up, forward
 // orchestration (include/diffsbdd_b200.h).  Host logic only + tiny packing kernels.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -99,13 +100,30 @@ struct Packer {
     if (!dry) { int64_t tot = (int64_t)N * K; pack_T_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(dst, ldd, dcol, src, lds, scol, N, K); }
     return dst;
   }
-  // tensor-core B images: allocate [Nn/256][K/32][8192] floats for hi and lo
-  void image_alloc(int Nn, int K, const float** hi, const float** lo, float** hi_w, float** lo_w) {
-    const size_t n = (size_t)(Nn / 256) * (K / 32) * 8192;
-    *hi_w = alloc(n); *lo_w = alloc(n); *hi = *hi_w; *lo = *lo_w;
-  }
-  void image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K) {
-    if (!dry) launch_pack_b_image(hi, lo, src, lds, scol, n_rows, n_dst_off, K);
+  // tensor-core operand images of one B[Nn][K] matrix assembled from `nblk` row blocks of the reference weights
+  // (src, lds, scol, n_rows, n_dst_off).  Builds the TF32 and the FP16 split images; the FP16 scale is the power of two
+  // that puts max|w| into [4096, 8192) so that the low part of every non-tiny weight is a normal fp16.
+  struct Blk { const float* src; int lds, scol, n_rows, n_dst_off; };
+  unsigned* d_absmax = nullptr;
+  void image(TcImage* img, int Nn, int K, const Blk* blk, int nblk) {
+    const size_t nt = (size_t)(Nn / 256) * (K / 32) * 8192;      // floats per TF32 image (hi or lo)
+    const size_t nh = (size_t)(Nn / 256) * (K / 64) * 8192;      // 32-bit words per FP16 image
+    float* thi = alloc(nt); float* tlo = alloc(nt); float* hhi = alloc(nh); float* hlo = alloc(nh);
+    img->t_hi = thi; img->t_lo = tlo; img->h_hi = hhi; img->h_lo = hlo; img->h_inv = 1.0f;
+    if (dry) return;
+    if (!d_absmax) cudaMalloc(&d_absmax, sizeof(unsigned));
+    cudaMemset(d_absmax, 0, sizeof(unsigned));
+    for (int i = 0; i < nblk; ++i) launch_absmax(blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, K, d_absmax);
+    unsigned bits = 0;
+    cudaMemcpy(&bits, d_absmax, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    float amax; memcpy(&amax, &bits, sizeof(float));
+    float scale = 1.0f;
+    if (amax > 0.f && amax < 3.0e38f) { int e; frexpf(amax, &e); scale = ldexpf(1.0f, 13 - e); }   // amax*scale in [4096, 8192)
+    img->h_inv = 1.0f / scale;     // activation scale X_SCALE is 1
+    for (int i = 0; i < nblk; ++i) {
+      launch_pack_b_image(thi, tlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K);
+      launch_pack_b_image_f16(hhi, hlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K, scale);
+    }
   }
   const float* copy(const float* src, int64_t n) {
     float* d = alloc(n);
@@ -174,18 +192,17 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
       G.b3 = cp(g + ".node_mlp.0.bias");
       { float* t = pk.alloc((size_t)H * H); G.W4 = pk.T(P(g + ".node_mlp.2.weight"), H, 0, H, H, t, H, 0); }
       G.b4 = cp(g + ".node_mlp.2.bias");
-      G.W1ab_hi = G.W1ab_lo = G.W2_hi = G.W2_lo = G.W3_hi = G.W3_lo = G.W4_hi = G.W4_lo = nullptr;
+      G.iW1ab = G.iW2 = G.iW3 = G.iW4 = TcImage{nullptr, nullptr, nullptr, nullptr, 1.0f};
       if (H == 256) {
-        float *hi, *lo;
-        pk.image_alloc(2 * H, H, &G.W1ab_hi, &G.W1ab_lo, &hi, &lo);
-        pk.image(hi, lo, P(g + ".edge_mlp.0.weight"), ld1, 0, H, 0, H);        // receiver part -> columns 0..H-1
-        pk.image(hi, lo, P(g + ".edge_mlp.0.weight"), ld1, H, H, H, H);        // sender part   -> columns H..2H-1
-        pk.image_alloc(H, H, &G.W2_hi, &G.W2_lo, &hi, &lo);
-        pk.image(hi, lo, P(g + ".edge_mlp.2.weight"), H, 0, H, 0, H);
-        pk.image_alloc(H, 2 * H, &G.W3_hi, &G.W3_lo, &hi, &lo);
-        pk.image(hi, lo, P(g + ".node_mlp.0.weight"), 2 * H, 0, H, 0, 2 * H);
-        pk.image_alloc(H, H, &G.W4_hi, &G.W4_lo, &hi, &lo);
-        pk.image(hi, lo, P(g + ".node_mlp.2.weight"), H, 0, H, 0, H);
+        const float* W1 = P(g + ".edge_mlp.0.weight");
+        Packer::Blk b1[2] = {{W1, ld1, 0, H, 0}, {W1, ld1, H, H, H}};     // receiver part -> columns 0..H-1, sender -> H..2H-1
+        pk.image(&G.iW1ab, 2 * H, H, b1, 2);
+        Packer::Blk b2 = {P(g + ".edge_mlp.2.weight"), H, 0, H, 0};
+        pk.image(&G.iW2, H, H, &b2, 1);
+        Packer::Blk b3 = {P(g + ".node_mlp.0.weight"), 2 * H, 0, H, 0};
+        pk.image(&G.iW3, H, 2 * H, &b3, 1);
+        Packer::Blk b4 = {P(g + ".node_mlp.2.weight"), H, 0, H, 0};
+        pk.image(&G.iW4, H, H, &b4, 1);
       }
     }
     const std::string q = b + ".gcl_equiv";
@@ -205,20 +222,20 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     }
     Q.W1 = W1; Q.b1 = b1;
     Q.w3 = cp(q + ".coord_mlp.4.weight");
-    Q.W1_hi = Q.W1_lo = nullptr;
-    for (int m = 0; m < 2; ++m) Q.W2_hi[m] = Q.W2_lo[m] = nullptr;
+    Q.iW1 = Q.iW2[0] = Q.iW2[1] = TcImage{nullptr, nullptr, nullptr, nullptr, 1.0f};
     if (H == 256) {
-      float *hi, *lo;
-      pk.image_alloc(nm * 2 * H, H, &Q.W1_hi, &Q.W1_lo, &hi, &lo);
+      Packer::Blk blk[4];
       for (int m = 0; m < nm; ++m) {
-        pk.image(hi, lo, P(q + names[m] + ".0.weight"), ld1, 0, H, m * 2 * H, H);
-        pk.image(hi, lo, P(q + names[m] + ".0.weight"), ld1, H, H, m * 2 * H + H, H);
-        float *h2, *l2;
-        pk.image_alloc(H, H, &Q.W2_hi[m], &Q.W2_lo[m], &h2, &l2);
-        pk.image(h2, l2, P(q + names[m] + ".2.weight"), H, 0, H, 0, H);
+        const float* W = P(q + names[m] + ".0.weight");
+        blk[2 * m] = {W, ld1, 0, H, m * 2 * H};
+        blk[2 * m + 1] = {W, ld1, H, H, m * 2 * H + H};
+        Packer::Blk b2 = {P(q + names[m] + ".2.weight"), H, 0, H, 0};
+        pk.image(&Q.iW2[m], H, H, &b2, 1);
       }
+      pk.image(&Q.iW1, nm * 2 * H, H, blk, 2 * nm);
     }
   }
+  if (pk.d_absmax) cudaFree(pk.d_absmax);
   *floats_out = pk.used;
   return 0;
 }
@@ -456,8 +473,9 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   };
 #define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
   const int mm = (H == 256) ? dyn->math_mode : 0;
-  auto gemm = [&](const GemmArgs& ga, const float* bhi, const float* blo) -> int {
-    return ((mm & 1) && bhi) ? launch_tc_node_gemm(dyn, ga, bhi, blo, s) : launch_node_gemm(ga, s);
+  const bool f16 = (mm & 8) != 0;
+  auto gemm = [&](const GemmArgs& ga, const TcImage& img) -> int {
+    return ((mm & 1) && img.t_hi) ? launch_tc_node_gemm(dyn, ga, img, f16, status, s) : launch_node_gemm(ga, s);
   };
 
   mark(KC_SETUP);
@@ -472,27 +490,27 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       const GclW& G = dyn->w.gcl[l][sub];
       mark(KC_NODE_GEMM);
       GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0};
-      DSB_TRY(gemm(g1, G.W1ab_hi, G.W1ab_lo));
+      DSB_TRY(gemm(g1, G.iW1ab));
       mark(KC_MEMSET);
       DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
       mark(KC_EDGE_GCL);
-      DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, s));
+      DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
       GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1};
-      DSB_TRY(gemm(g2, G.W3_hi, G.W3_lo));
+      DSB_TRY(gemm(g2, G.iW3));
       GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0};
-      DSB_TRY(gemm(g3, G.W4_hi, G.W4_lo));
+      DSB_TRY(gemm(g3, G.iW4));
       launches += 4; memsets += 1;
     }
     const EquivW& Q = dyn->w.eq[l];
     mark(KC_NODE_GEMM);
     GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, nm * 2 * H, Q.b1, nullptr, 0, ws.P, nm * 2 * H, dm.N, nm * 2 * H, 0};
-    DSB_TRY(gemm(g4, Q.W1_hi, Q.W1_lo));
+    DSB_TRY(gemm(g4, Q.iW1));
     mark(KC_MEMSET);
     DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
     mark(KC_EDGE_COORD);
-    DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, s));
+    DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, f16, status, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];
     mark(KC_COORD_FINISH);
     DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
@@ -511,7 +529,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
 
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {
   if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
-  if (mode < 0 || mode > 7) { set_error("math mode must be a bitmask in [0,7]"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (mode < 0 || mode > 15) { set_error("math mode must be a bitmask in [0,15]"); return DSB_ERR_INVALID_ARGUMENT; }
   if (mode != 0 && dyn->cfg.hidden_nf != 256) { set_error("the tcgen05 3xTF32 path is built for hidden_nf=256 only"); return DSB_ERR_UNSUPPORTED_CONFIG; }
   dyn->math_mode = mode;
   return 0;

@@ -12,6 +12,16 @@ namespace dsb {
 constexpr int kMaxSub = 4;      // inv_sublayers supported per block
 constexpr int kMaxLayers = 16;
 
+// tensor-core operand images of one weight matrix B[n][k] (H == 256 only; all nullptr otherwise):
+//   t_*: TF32 hi/lo split, [Nn/256][K/32][256 rows x 128 B SWIZZLE_128B]
+//   h_*: FP16 hi/lo split of w * h_scale, [Nn/256][K/64][256 rows x 128 B]; h_inv = 1 / h_scale undoes the
+//        weight scale and the activation scale in the epilogue (both powers of two: exact)
+struct TcImage {
+  const float *t_hi, *t_lo;
+  const float *h_hi, *h_lo;
+  float h_inv;
+};
+
 // ---- packed weights (device pointers into one blob; all GEMM operands k-major: W[k][n]) -------------
 struct GclW {            // one GCL (reference egnn_new.py:6-66)
   const float* W1ab;     // [H][2H]  cols 0..H-1: edge_mlp.0.weight[:, 0:H]^T (receiver h_i), H..2H-1: [:, H:2H]^T (sender h_j)
@@ -27,11 +37,7 @@ struct GclW {            // one GCL (reference egnn_new.py:6-66)
   const float* b3;       // [H]
   const float* W4;       // [H][H]   node_mlp.2.weight^T
   const float* b4;       // [H]
-  // tensor-core operand images (H == 256 only; nullptr otherwise): hi/lo TF32 split of B[n][k], [n_tile][k_chunk][256x128B swizzled]
-  const float *W1ab_hi, *W1ab_lo;   // Nn = 2H, K = H
-  const float *W2_hi, *W2_lo;       // Nn = H,  K = H
-  const float *W3_hi, *W3_lo;       // Nn = H,  K = 2H
-  const float *W4_hi, *W4_lo;       // Nn = H,  K = H
+  TcImage iW1ab, iW2, iW3, iW4;   // Nn x K = 2H x H, H x H, H x 2H, H x H
 };
 
 struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); index 0 = coord_mlp, 1 = cross_product_mlp
@@ -43,8 +49,8 @@ struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); in
   const float* W2[2];    // [H][H]
   const float* b2[2];    // [H]
   const float* w3;       // [H] shared bias-free last layer (egnn_new.py:78)
-  const float *W1_hi, *W1_lo;       // tensor-core images, Nn = nm*2H, K = H
-  const float *W2_hi[2], *W2_lo[2]; // Nn = H, K = H
+  TcImage iW1;                      // Nn = nm*2H, K = H
+  TcImage iW2[2];                   // Nn = H, K = H
 };
 
 struct PackedWeights {
@@ -95,7 +101,7 @@ struct dsb_dynamics {
   float* blob = nullptr;
   size_t blob_floats = 0;
   int num_sms = 148;
-  int math_mode = 0;         // bitmask: 1 node GEMMs, 2 edge_gcl, 4 edge_coord on the tcgen05 3xTF32 path (H == 256)
+  int math_mode = 0;         // bitmask: 1 node GEMMs, 2 edge_gcl, 4 edge_coord on tcgen05 (H == 256); 8: 3xFP16 split instead of 3xTF32
   int last_launches = 0;     // kernels only
   int last_memsets = 0;
   // profiling
@@ -152,16 +158,24 @@ int configure_edge_kernels(int H);
 
 // ---- tensor-core path (dsb_tc.cu) --------------------------------------------------------------------
 void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K);
+void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale);
+void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsigned* out);
 int configure_tc_kernels();
-int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const float* bhi, const float* blo, cudaStream_t s);
-int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, cudaStream_t s);
-int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, cudaStream_t s);
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, bool f16, int32_t* status, cudaStream_t s);
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, bool f16,
+                       int32_t* status, cudaStream_t s);
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, bool f16,
+                         int32_t* status, cudaStream_t s);
 
 // ---- device math helpers ----------------------------------------------------------------------------
-// SiLU / sigmoid via MUFU.EX2 + MUFU.RCP: relative error ~2 ulp + |x|*6e-8 from the exponent scaling,
-// i.e. at the fp32 noise floor of the reference itself (3e-7).
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// SiLU / sigmoid as FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL (ex2.approx / rcp.approx, ~2 ulp each): relative error
+// ~3e-7 + |x|*6e-8 from the exponent scaling, i.e. at the fp32 noise floor of the reference itself.
+// The libdevice forms (__expf/__fdividef) add range fix-ups (FSETP + 2 FMUL each) that double the instruction count
+// of the hot loops for inputs that never occur here (|pre-activation| > 87).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

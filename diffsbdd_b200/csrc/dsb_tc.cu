@@ -40,6 +40,47 @@ void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int sc
   pack_b_image_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(hi, lo, src, lds, scol, n_rows, n_dst_off, K, K / TKC);
 }
 
+// 3xFP16 images: w*scale = w_h + w_l in fp16, [n_tile][K/64][256 rows x 128 B (64 halfs), SWIZZLE_128B]
+__global__ void pack_b_image_f16_kernel(__half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ src, int lds,
+                                        int scol, int n_rows, int n_dst_off, int K, int chunks, float scale) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_rows * K) return;
+  const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K);
+  const int nd = n_dst_off + n, nt = nd / TN, nl = nd % TN;
+  const int kc = k / TKC16, c16 = (k % TKC16) >> 3, j = k & 7;
+  const size_t off = ((size_t)nt * chunks + kc) * (B_CHUNK_BYTES / 2) + sw128_offset(nl, c16) / 2 + j;
+  const float w = src[(size_t)n * lds + scol + k] * scale;
+  const __half h = __float2half_rn(w);
+  hi[off] = h;
+  lo[off] = __float2half_rn(w - __half2float(h));
+}
+
+void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale) {
+  const int64_t tot = (int64_t)n_rows * K;
+  pack_b_image_f16_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), src,
+                                                                  lds, scol, n_rows, n_dst_off, K, K / TKC16, scale);
+}
+
+// max |src[n][scol + k]| over an [n_rows][K] block -> *out (device uint holding the float bits; non-negative floats order as uints)
+__global__ void absmax_kernel(const float* __restrict__ src, int lds, int scol, int n_rows, int K, unsigned* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (idx < (int64_t)n_rows * K) { const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K); v = fabsf(src[(size_t)n * lds + scol + k]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(v));
+}
+void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsigned* out) {
+  const int64_t tot = (int64_t)n_rows * K;
+  absmax_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(src, lds, scol, n_rows, K, out);
+}
+
+// bring-up / diagnosis only (profiles/tc_ablate.py): 1 skip weight copies, 2 skip producer work, 4 skip epilogue work,
+// 8 skip MMAs.  Results are garbage when non-zero; never set by the product path.
+extern "C" int dsb_debug_set_tc_flags(int flags) {
+  return cudaMemcpyToSymbol(tc::g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -3;
+}
+
 // ---- common prologue / epilogue of every TC kernel -----------------------------------------------------------------
 constexpr size_t kControlBytes = 128;      // keeps the per-kernel extras 16-byte aligned for float4 access
 static_assert(sizeof(Control) <= kControlBytes, "Control block grew");
@@ -79,6 +120,7 @@ __device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float
     const int s = g & 1;
     mbar_wait(&ctl->empty[s], ((g >> 1) & 1) ^ 1);
     char* st = stages + (size_t)s * STAGE_BYTES + 2 * A_CHUNK_BYTES;
+    if (g_tc_debug & 1) { mbar_arrive(&ctl->full_w[s]); continue; }
     mbar_arrive_expect_tx(&ctl->full_w[s], 2 * B_CHUNK_BYTES);
     bulk_g2s(st, bhi + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
     bulk_g2s(st + B_CHUNK_BYTES, blo + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
@@ -94,8 +136,11 @@ struct TcGemmArgs {
   const float* Bhi; const float* Blo;        // [Nn/256][K/32][8192]
   const float* bias; const float* R; int ldr;
   float* C; int ldc; int M; int Nn; int act;
+  float inv_scale;                             // 3xFP16: 1 / (X_SCALE * weight scale); 1 for 3xTF32
+  int32_t* status;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw);
@@ -105,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
   const int n_tiles = ntn * ntm;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (n_my == 0) return;
-  const int K = g.K1 + g.K2, chunks = K / TKC;
+  const int K = g.K1 + g.K2, halves = K / TKC, chunks = F16 ? halves / 2 : halves;
   tc_begin(ctl, warp);
 
   if (warp < EPI_WARPS) {
@@ -124,6 +169,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
         tmem_ld32(taddr + cb * 32, v);
         if (row < g.M) {
           const int n = n0 + cb * 32;
+          if (F16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= g.inv_scale;
+          }
           if (g.bias) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -157,38 +206,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     const int ptid = threadIdx.x - EPI_WARPS * 32;
     const int pr = ptid >> 1, phf = ptid & 1;
     uint32_t gc = 0;
+    auto load_half = [&](int m, bool valid, int hf, float4 (&v)[4]) {
+      const int k = hf * TKC + phf * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          if (k < g.K1) {
+            x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k + 4 * q);
+          } else {
+            x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1) + 4 * q);
+            if (g.div2 != 1.0f) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
+          }
+        }
+        v[q] = x;
+      }
+    };
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int m = (tile / ntn) * TM + pr;
       const bool valid = m < g.M;
-      for (int kc = 0; kc < chunks; ++kc, ++gc) {
+      float4 cur[4], nxt[4];
+      load_half(m, valid, 0, cur);
+      for (int hf = 0; hf < halves; ++hf) {
+        if (hf + 1 < halves) load_half(m, valid, hf + 1, nxt);
         const int s = gc & 1;
-        float4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = kc * TKC + (phf + 2 * q) * 4;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) {
-            if (k < g.K1) {
-              x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k);
-            } else {
-              x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1));
-              if (g.div2 != 1.0f) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
-            }
-          }
-          v[q] = x;
+        if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+        store_row16<F16>(cv.stages + (size_t)s * STAGE_BYTES, pr, hf, phf, cur);
+        if (!F16 || (hf & 1)) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+          ++gc;
         }
-        mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-        char* st = cv.stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, pr, phf + 2 * q, v[q]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role(ctl, cv.stages, n_my, chunks);
+    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
     __syncwarp();
   } else {
     if (lane == 0) {
@@ -234,6 +290,8 @@ struct TcEdgeArgs {
   float norm_constant, coords_range; int use_tanh;
   float* agg;                                // GCL: [N][H] raw sums
   float4* xagg;                              // coord: [N] raw sums of trans
+  float inv_scale[2];                        // 3xFP16: 1 / (X_SCALE * W2 scale) per MLP; 1 for 3xTF32
+  int32_t* status;
 };
 
 // per-edge scalars of tile `e0`, written by the 128 even producer threads
@@ -269,7 +327,7 @@ __device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex,
 }
 
 // Virtual tile vt = tile * nm + m  (m-th MLP of the tile).  par(tile) selects the scalar buffers, a = vt & 1 the accumulator.
-template <bool COORD>
+template <bool COORD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw);
@@ -282,7 +340,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
   if (n_my_tiles == 0) return;
   const int nm = a.nm;
   const int n_my = n_my_tiles * nm;            // virtual tiles
-  constexpr int chunks = H256 / TKC;
+  constexpr int halves = H256 / TKC;           // 32-k production steps per virtual tile
+  constexpr int chunks = F16 ? halves / 2 : halves;
   const bool has_tb = a.tb[0] != nullptr;
 
   for (int i = threadIdx.x; i < H256; i += TC_THREADS) {
@@ -307,19 +366,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
       tc_fence_after();
       const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TN);
       const float* b2 = ex->vec[m] + 2 * H256;
+      const float inv = a.inv_scale[m];
       const int myrow = ex->row[par][warp * 32 + lane];
+      if (g_tc_debug & 4) {
+        tc_fence_before(); __syncwarp();
+        if (lane == 0) { mbar_arrive(&ctl->epi_done[acc]); if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]); }
+        continue;
+      }
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
       float s = 0.f;
+      const int edbg = g_tc_debug;
 #pragma unroll 1
       for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
         tmem_ld32(taddr + cb * 32, v);
+        if (!(edbg & 32))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(b2 + cb * 32 + 4 * q);
           const float4 ww = *reinterpret_cast<const float4*>(ex->wa + cb * 32 + 4 * q);
-          v[4 * q] = silu_f(v[4 * q] + bb.x); v[4 * q + 1] = silu_f(v[4 * q + 1] + bb.y);
-          v[4 * q + 2] = silu_f(v[4 * q + 2] + bb.z); v[4 * q + 3] = silu_f(v[4 * q + 3] + bb.w);
+          if (F16) {
+            v[4 * q] = silu_f(fmaf(v[4 * q], inv, bb.x)); v[4 * q + 1] = silu_f(fmaf(v[4 * q + 1], inv, bb.y));
+            v[4 * q + 2] = silu_f(fmaf(v[4 * q + 2], inv, bb.z)); v[4 * q + 3] = silu_f(fmaf(v[4 * q + 3], inv, bb.w));
+          } else {
+            v[4 * q] = silu_f(v[4 * q] + bb.x); v[4 * q + 1] = silu_f(v[4 * q + 1] + bb.y);
+            v[4 * q + 2] = silu_f(v[4 * q + 2] + bb.z); v[4 * q + 3] = silu_f(v[4 * q + 3] + bb.w);
+          }
           s = fmaf(v[4 * q], ww.x, s); s = fmaf(v[4 * q + 1], ww.y, s); s = fmaf(v[4 * q + 2], ww.z, s); s = fmaf(v[4 * q + 3], ww.w, s);
         }
         if (!COORD) tmem_st32(taddr + cb * 32, v);
@@ -327,31 +399,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
       if (!COORD) {
         tmem_wait_st();
         const float gate = has_att ? sigmoid_f(s + ba) : 1.0f;
-        // segment structure of this warp's 32 rows (uniform across the 8 column blocks)
+        // segment structure of this warp's 32 rows (uniform across the 8 column blocks): segment k covers rows
+        // [seg_lo[k], seg_lo[k+1]) with receiver seg_row[k]; at most 32 segments, typically 1-3.
         const int prev = __shfl_up_sync(0xffffffffu, myrow, 1);
         const unsigned seg_start = __ballot_sync(0xffffffffu, lane == 0 || myrow != prev);
         // pass 2: e = m * gate -> transpose through shared memory -> in-order segmented column sums -> RED
 #pragma unroll 1
-        for (int cb = 0; cb < TN / 32; ++cb) {
+        for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
           tmem_ld32(taddr + cb * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * EPI_T_STRIDE + j] = v[j] * gate;
           __syncwarp();
-          float sum = 0.f;
           float* dst = a.agg + cb * 32 + lane;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr > 0 && ((seg_start >> rr) & 1u)) {
-              const int prow = __shfl_sync(0xffffffffu, myrow, rr - 1);
-              if (prow >= 0) atomicAdd(dst + (size_t)prow * H256, sum);
-              sum = 0.f;
-            }
-            sum += T[rr * EPI_T_STRIDE + lane];
-          }
-          {
-            const int prow = __shfl_sync(0xffffffffu, myrow, 31);
-            if (prow >= 0) atomicAdd(dst + (size_t)prow * H256, sum);
+          unsigned rest = seg_start;
+#pragma unroll 1
+          while (rest) {                       // one iteration per receiver segment (warp-uniform control flow)
+            const int r0 = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const int r1 = rest ? __ffs(rest) - 1 : 32;
+            const int prow = __shfl_sync(0xffffffffu, myrow, r0);
+            float sum = 0.f;
+#pragma unroll 4
+            for (int rr = r0; rr < r1; ++rr) sum += T[rr * EPI_T_STRIDE + lane];
+            if (prow >= 0 && !(edbg & 64)) atomicAdd(dst + (size_t)prow * H256, sum);
           }
           __syncwarp();
         }
@@ -403,6 +474,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
     // ------------------------------------------------------------------------------------------ producers
     const int ptid = threadIdx.x - EPI_WARPS * 32;
     const int pr = ptid >> 1, phf = ptid & 1;
+    const int dbg = g_tc_debug;
     uint32_t gc = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int par = it & 1;
@@ -416,24 +488,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
       const float pd2 = ex->d2[par][pr], pd0 = ex->d0[par][pr];
       const int ptype = ex->type[par][pr];
       for (int m = 0; m < nm; ++m) {
-        const float* Pa = a.P + (size_t)prow * a.ldp + m * 2 * H256;
-        const float* Pb = a.P + (size_t)pcol * a.ldp + m * 2 * H256 + H256;
-        const float* wr = ex->vec[m]; const float* wr0 = wr + H256;
-        const float* tb = has_tb ? a.tb[m] + ptype * H256 : nullptr;
+        const float* Pa = a.P + (size_t)prow * a.ldp + m * 2 * H256 + phf * 16;
+        const float* Pb = a.P + (size_t)pcol * a.ldp + m * 2 * H256 + H256 + phf * 16;
+        const float* wr = ex->vec[m] + phf * 16; const float* wr0 = wr + H256;
+        const float* tb = has_tb ? a.tb[m] + ptype * H256 + phf * 16 : nullptr;
         float4 ga[4], gb[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int k0 = (phf + 2 * q) * 4;
-          ga[q] = *reinterpret_cast<const float4*>(Pa + k0);
-          gb[q] = *reinterpret_cast<const float4*>(Pb + k0);
+          ga[q] = *reinterpret_cast<const float4*>(Pa + 4 * q);
+          gb[q] = *reinterpret_cast<const float4*>(Pb + 4 * q);
         }
 #pragma unroll 1
-        for (int kc = 0; kc < chunks; ++kc, ++gc) {
+        for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
           float4 v[4];
+          if (dbg & 2) { v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
+          else
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int k0 = kc * TKC + (phf + 2 * q) * 4;
+            const int k0 = hf * TKC + 4 * q;
             const float4 r4 = *reinterpret_cast<const float4*>(wr + k0);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + k0);
             float u0 = fmaf(pd0, r04.x, fmaf(pd2, r4.x, ga[q].x + gb[q].x));
@@ -446,26 +519,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
             }
             v[q] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
           }
-          if (kc + 1 < chunks) {
+          if (hf + 1 < halves && !(dbg & (2 | 128))) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int k0 = (kc + 1) * TKC + (phf + 2 * q) * 4;
-              ga[q] = *reinterpret_cast<const float4*>(Pa + k0);
-              gb[q] = *reinterpret_cast<const float4*>(Pb + k0);
+              ga[q] = *reinterpret_cast<const float4*>(Pa + (hf + 1) * TKC + 4 * q);
+              gb[q] = *reinterpret_cast<const float4*>(Pb + (hf + 1) * TKC + 4 * q);
             }
           }
-          mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-          char* st = cv.stages + (size_t)s * STAGE_BYTES;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, pr, phf + 2 * q, v[q]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+          if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+          if (!(dbg & (2 | 256))) store_row16<F16>(cv.stages + (size_t)s * STAGE_BYTES, pr, hf, phf, v);
+          if (!F16 || (hf & 1)) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+            ++gc;
+          }
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role(ctl, cv.stages, n_my, chunks);
+    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
     __syncwarp();
   } else {
     if (lane == 0) {
@@ -487,52 +560,67 @@ static size_t gemm_smem_bytes() { return kTcSmemBase; }
 static size_t edge_smem_bytes() { return kTcSmemBase + sizeof(EdgeExtra); }
 
 int configure_tc_kernels() {
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
   return 0;
 }
 
-int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const float* bhi, const float* blo, cudaStream_t s) {
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, bool f16, int32_t* status, cudaStream_t s) {
   if (g.M == 0) return 0;
   const int K = g.K1 + g.K2;
-  if ((g.Nn % TN) || (K % TKC) || (g.K1 % TKC) || (g.lda1 % 4) || (g.ldc % 4)) {
+  if ((g.Nn % TN) || (K % TKC16) || (g.K1 % TKC16) || (g.lda1 % 4) || (g.ldc % 4)) {
     set_error("tc_node_gemm: unsupported shape K1=%d K2=%d Nn=%d", g.K1, g.K2, g.Nn);
     return DSB_ERR_INVALID_ARGUMENT;
   }
   TcGemmArgs a;
   a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2;
-  a.Bhi = bhi; a.Blo = blo; a.bias = g.bias; a.R = g.R; a.ldr = g.ldr; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.Nn = g.Nn; a.act = g.act;
+  a.Bhi = f16 ? w.h_hi : w.t_hi; a.Blo = f16 ? w.h_lo : w.t_lo;
+  a.bias = g.bias; a.R = g.R; a.ldr = g.ldr; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.Nn = g.Nn; a.act = g.act;
+  a.inv_scale = f16 ? w.h_inv : 1.0f; a.status = status;
   const int n_tiles = (g.Nn / TN) * ((g.M + TM - 1) / TM);
   const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
-  tc_node_gemm_kernel<<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
+  if (f16) tc_node_gemm_kernel<true><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
+  else tc_node_gemm_kernel<false><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, cudaStream_t s) {
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, bool f16,
+                       int32_t* status, cudaStream_t s) {
   TcEdgeArgs a = {};
   a.P = ws.P; a.ldp = 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.N;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.nm = 1;
-  a.W2hi[0] = w.W2_hi; a.W2lo[0] = w.W2_lo; a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
-  a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg;
-  tc_edge_kernel<false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  a.W2hi[0] = f16 ? w.iW2.h_hi : w.iW2.t_hi; a.W2lo[0] = f16 ? w.iW2.h_lo : w.iW2.t_lo;
+  a.inv_scale[0] = f16 ? w.iW2.h_inv : 1.0f; a.inv_scale[1] = 1.0f;
+  a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
+  a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg; a.status = status;
+  if (f16) tc_edge_kernel<false, true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  else tc_edge_kernel<false, false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, cudaStream_t s) {
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, bool f16,
+                         int32_t* status, cudaStream_t s) {
   const dsb_config& c = d->cfg;
   TcEdgeArgs a = {};
   a.nm = c.reflection_equivariant ? 1 : 2;
   a.P = ws.P; a.ldp = a.nm * 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL;
+  a.inv_scale[0] = a.inv_scale[1] = 1.0f;
   for (int m = 0; m < a.nm; ++m) {
-    a.W2hi[m] = w.W2_hi[m]; a.W2lo[m] = w.W2_lo[m]; a.wr[m] = w.wr[m]; a.wr0[m] = w.wr0[m]; a.tb[m] = w.tb[m]; a.b2[m] = w.b2[m];
+    a.W2hi[m] = f16 ? w.iW2[m].h_hi : w.iW2[m].t_hi; a.W2lo[m] = f16 ? w.iW2[m].h_lo : w.iW2[m].t_lo;
+    a.inv_scale[m] = f16 ? w.iW2[m].h_inv : 1.0f;
+    a.wr[m] = w.wr[m]; a.wr0[m] = w.wr0[m]; a.tb[m] = w.tb[m]; a.b2[m] = w.b2[m];
   }
   a.wa = w.w3; a.ba = nullptr;
-  a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg;
-  tc_edge_kernel<true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg; a.status = status;
+  if (f16) tc_edge_kernel<true, true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  else tc_edge_kernel<true, false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,6 +1,10 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the shared pipeline pieces of the tensor-core path.
 //
-// Numerics: every contraction is a 3xTF32 split product accumulated in fp32 inside TMEM:
+// Numerics: every contraction is a 3-product split accumulated in fp32 inside TMEM, in one of two operand formats:
+//   3xTF32 (kind::tf32, 4 B/operand element, 8-bit exponent: range-robust), or
+//   3xFP16 (kind::f16,  2 B/operand element: half the shared-memory operand traffic and twice the MMA rate; operands are
+//           pre-scaled by powers of two so residuals stay in fp16's normal range; |16 x| > 60000 raises a status flag).
+// 3xTF32:
 //     a = a_hi + a_lo,  a_hi = cvt.rna.tf32(a),  a_lo = a - a_hi   (exact; the MMA truncates a_lo to 11 bits: 2^-23 |a|)
 //     a.b ~= a_lo.b_hi + a_hi.b_lo + a_hi.b_hi                       (dropped a_lo.b_lo ~ 2^-24 |a||b|)
 // which keeps fp32-grade accuracy (the parity tolerance is atol 1e-5 / rtol 1e-4; plain TF32 would be ~1e-3).
@@ -10,6 +14,8 @@
 // One tcgen05.mma kind::tf32 consumes K=8 (32 bytes); stepping K inside the swizzled row = advancing the descriptor
 // start address by 32 bytes.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "dsb_internal.cuh"
 
 namespace dsb {
@@ -17,7 +23,10 @@ namespace tc {
 
 constexpr int TM = 128;            // rows (edges / nodes) per tile = TMEM lanes
 constexpr int TN = 256;            // accumulator columns per tile
-constexpr int TKC = 32;            // k-values per chunk (one 128B swizzle row)
+constexpr int TKC = 32;            // k-values per 128-byte swizzle row with 4-byte (TF32) operands
+constexpr int TKC16 = 64;          // ... with 2-byte (FP16) operands
+constexpr float X_SCALE = 1.0f;    // 3xFP16 activation scale (1: |x| < 0.25 has a subnormal fp16 residual, abs. error <= 3e-8)
+constexpr float F16_LIMIT = 60000.0f;
 constexpr int A_CHUNK_BYTES = TM * 128;        // 16 KB
 constexpr int B_CHUNK_BYTES = TN * 128;        // 32 KB
 constexpr int B_CHUNK_FLOATS = TN * TKC;       // 8192
@@ -33,6 +42,8 @@ constexpr int PROD_THREADS = PROD_WARPS * 32;           // 256
 
 // instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128  (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t IDESC_TF32_M128_N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+// same with A=B=F16 (format code 0)
+constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4) | (0u << 7) | (0u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -119,6 +130,29 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       : "memory");
 }
 
+// split form for software pipelining: issue now, consume after tmem_ld32_wait(r).  The wait carries the 32 registers as
+// in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------------------------------
 // K-major SWIZZLE_128B shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 |
 // version 1 <<46 | layout SWIZZLE_128B(2) <<61
@@ -132,16 +166,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  return __uint_as_float(h);
-}
+// round-to-nearest (ties away) to the 19-bit TF32 container with two integer-pipe instructions (cvt.rna.tf32.f32
+// would occupy the 16-lane XU pipe that the SiLU exponentials already saturate)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // byte offset of (row r, 16-byte chunk c) inside a [rows][128 B] SWIZZLE_128B tile
 __device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int c) {
@@ -155,6 +194,41 @@ __device__ __forceinline__ void store_split(char* a_hi, char* a_lo, int row, int
   const uint32_t off = sw128_offset(row, chunk);
   *reinterpret_cast<float4*>(a_hi + off) = h;
   *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
+// 3xFP16 producer helper: 8 consecutive k-values (two float4, already multiplied by X_SCALE) -> 16-byte chunk c16 of the
+// row in the hi and lo tiles.  x_h = fp16_rn(x), x_l = fp16_rn(x - x_h): 22 significand bits while x_l is a normal fp16.
+__device__ __forceinline__ void store_split_f16(char* a_hi, char* a_lo, int row, int c16, float4 v0, float4 v1) {
+  const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+  const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+  const __half2 l0 = __floats2half2_rn(v0.x - f0.x, v0.y - f0.y), l1 = __floats2half2_rn(v0.z - f1.x, v0.w - f1.y);
+  const __half2 l2 = __floats2half2_rn(v1.x - f2.x, v1.y - f2.y), l3 = __floats2half2_rn(v1.z - f3.x, v1.w - f3.y);
+  const uint32_t off = sw128_offset(row, c16);
+  uint4 hv, lv;
+  hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+  hv.z = *reinterpret_cast<const uint32_t*>(&h2); hv.w = *reinterpret_cast<const uint32_t*>(&h3);
+  lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+  lv.z = *reinterpret_cast<const uint32_t*>(&l2); lv.w = *reinterpret_cast<const uint32_t*>(&l3);
+  *reinterpret_cast<uint4*>(a_hi + off) = hv;
+  *reinterpret_cast<uint4*>(a_lo + off) = lv;
+}
+
+// Producer-side store of 16 consecutive k-values of one row (k = half*32 + phf*16 + 0..15 of the tile's K range).
+//   TF32: chunk (stage) = one 32-k half; four 16-byte stores per operand at chunk positions phf*4 + q
+//   FP16: chunk (stage) = two halves (64 k); two 16-byte stores per operand at positions (half&1)*4 + phf*2 + j
+template <bool F16>
+__device__ __forceinline__ void store_row16(char* st, int row, int half, int phf, const float4 (&v)[4]) {
+  if constexpr (F16) {
+    // An activation beyond the fp16 range becomes inf here and reaches the output as NaN -> the NaN guard of the
+    // denoiser raises (dynamics.py:155-159 convention); 3xTF32 has no such limit.
+    const int c0 = (half & 1) * 4 + phf * 2;
+    store_split_f16(st, st + A_CHUNK_BYTES, row, c0, v[0], v[1]);
+    store_split_f16(st, st + A_CHUNK_BYTES, row, c0 + 1, v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, row, phf * 4 + q, v[q]);
+  }
 }
 
 // ---- shared-memory control block -------------------------------------------------------------------------------------
@@ -177,8 +251,12 @@ __device__ __forceinline__ void control_init(Control* c) {
 }
 
 // ---- MMA issuer (one thread): per tile, per chunk: 4 k-steps x 3 split products ------------------------------------------
+// bring-up / diagnosis switch (see dsb_tc.cu); this header is included by exactly one translation unit
+__device__ int g_tc_debug = 0;
+template <bool F16>
 __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile) {
   const uint32_t tmem = ctl->tmem_base;
+  const bool skip = (g_tc_debug & 8) != 0;
   uint32_t g = 0;
   for (int it = 0; it < n_my_tiles; ++it) {
     const int a = it & 1;
@@ -193,12 +271,19 @@ __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_ti
       tc_fence_after();
       char* st = stages + (size_t)s * STAGE_BYTES;
       const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
+      if (!skip)
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte row (K=8 tf32 or K=16 fp16 each)
         const uint32_t ko = ks * 32;
-        umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, (kc | ks) ? 1u : 0u);
-        umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
-        umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
+        if constexpr (F16) {
+          umma_f16(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, (kc | ks) ? 1u : 0u);
+          umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_F16_M128_N256, 1u);
+          umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, 1u);
+        } else {
+          umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, (kc | ks) ? 1u : 0u);
+          umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
+          umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
+        }
       }
       umma_commit(&ctl->empty[s]);          // stage reusable once these MMAs have read it
     }

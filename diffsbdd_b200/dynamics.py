@@ -148,8 +148,9 @@ class EGNNDynamics(nn.Module):
         self._workspace: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
         self.defer_status_check = False    # samplers that CUDA-graph the loop check once at the end
-        # arithmetic path: bitmask 1 node GEMMs | 2 edge kernel | 4 coordinate kernel on tcgen05 (3xTF32, fp32-grade),
-        # 0 = fp32 FFMA kernels.  'auto' = 7 when hidden_nf == 256 (the only width with tensor-core kernels), else 0.
+        # arithmetic path: bitmask 1 node GEMMs | 2 edge kernel | 4 coordinate kernel on tcgen05, 8 = 3xFP16 operand split
+        # instead of 3xTF32; 0 = fp32 FFMA kernels.  Names: 'fp32' (0), '3xtf32' (7), '3xfp16' (15).
+        # 'auto' = '3xfp16' when hidden_nf == 256 (the only width with tensor-core kernels), else 'fp32'.
         self._math_mode = os.environ.get('DSB_MATH_MODE', 'auto')
         self.to(device)
 
@@ -173,11 +174,13 @@ class EGNNDynamics(nn.Module):
     def math_mode(self) -> int:
         m = self._math_mode
         if m in ('auto', None):
-            return 7 if self.cfg.hidden_nf == 256 else 0
+            return 15 if self.cfg.hidden_nf == 256 else 0
         if m == 'fp32':
             return 0
         if m == '3xtf32':
             return 7
+        if m == '3xfp16':
+            return 15
         return int(m)
 
     @math_mode.setter
@@ -254,10 +257,12 @@ class EGNNDynamics(nn.Module):
         if self._status is None:
             return
         flags = self._status.tolist()
-        if flags[0] or flags[2]:
+        if flags[0] or flags[2] or flags[3]:
             self._status.zero_()
         if flags[2]:
             raise RuntimeError('edge list overflowed edge_capacity (internal error)')
+        if flags[3]:
+            raise RuntimeError("an activation exceeded the fp16 range of math_mode='3xfp16'; set math_mode='3xtf32'")
         if flags[0]:
             raise ValueError('NaN detected in EGNN output')
 

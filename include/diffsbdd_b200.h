@@ -93,8 +93,9 @@ size_t dsb_dynamics_workspace_bytes(const dsb_dynamics* dyn, int64_t n_atoms, in
  *   status      device int32[4]: [0] |= 1 if a NaN reached the coordinate output (the reference raises
  *               ValueError("NaN detected in EGNN output"), dynamics.py:155-159 — the host wrapper
  *               turns the flag into that exception); [1] = number of edges of this call;
- *               [2] |= 1 if the edge list would not fit edge_capacity (outputs invalid). Sticky: the
- *               library only ORs into [0] and [2], the caller clears them.
+ *               [2] |= 1 if the edge list would not fit edge_capacity (outputs invalid); [3] |= 1 if an activation left
+ *               the fp16 range in 3xFP16 mode (outputs invalid: rerun with 3xTF32).  Sticky: the library only ORs into
+ *               [0], [2], [3]; the caller clears them.
  * Inputs are not modified.  Asynchronous on `stream` (a cudaStream_t passed as void*). */
 int dsb_dynamics_forward(dsb_dynamics* dyn,
                          const float* xh_atoms, const float* xh_residues,
@@ -121,9 +122,12 @@ int dsb_dynamics_edges(dsb_dynamics* dyn,
 int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
 
 /* ---- arithmetic path.  mode is a bitmask: 1 = node GEMMs, 2 = edge (GCL) kernel, 4 = coordinate edge kernel run on
- * the tensor pipe (tcgen05.mma kind::tf32, 3xTF32 split products hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM:
- * fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance); 0 = fp32 FFMA kernels everywhere.
- * Only hidden_nf == 256 has tensor-core kernels; other widths must use 0. */
+ * the tensor pipe (tcgen05.mma, accumulators in TMEM) as 3-product split contractions with fp32 accumulation
+ * (x.w ~= x_lo.w_hi + x_hi.w_lo + x_hi.w_hi: fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance);
+ * 8 selects the operand format of those kernels: 0 = 3xTF32 (kind::tf32, 8-bit exponent, any range),
+ * 8 = 3xFP16 (kind::f16: half the shared-memory operand traffic, twice the MMA rate; weights are pre-scaled per matrix
+ * and activations by 16 with exact powers of two; an activation with |16 x| > 60000 sets status[3] and the host
+ * wrapper raises).  0 = fp32 FFMA kernels everywhere.  Only hidden_nf == 256 has tensor-core kernels. */
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode);
 
 /* ---- measurement hook (bench.py's live roofline).  When enabled, every non-captured forward brackets

@@ -36,11 +36,12 @@ def test_golden_edges_bit_exact(case):
     assert got.shape == edges.shape and torch.equal(got, edges)
 
 
-@pytest.mark.parametrize('mode', ['fp32', 1, 2, 4])
+@pytest.mark.parametrize('mode', ['fp32', '3xtf32', 1, 2, 4, 9, 10, 12])
 @pytest.mark.parametrize('case', ['config1_n64_l4', 'ragged_b3_l4', 'fullatom_b2_n200_l6', 'ca_b3_l6'])
 def test_golden_forward_every_math_mode(case, mode):
-    """hidden_nf=256 cases through each arithmetic path: fp32 FFMA kernels, and the tcgen05 3xTF32 node GEMMs (1),
-    edge kernel (2), coordinate kernel (4) individually (the default 'auto' = all three is covered by test_golden_forward)."""
+    """hidden_nf=256 cases through each arithmetic path: fp32 FFMA kernels; tcgen05 3xTF32 everywhere; and the node
+    GEMMs (1), edge kernel (2), coordinate kernel (4) individually in 3xTF32 and in 3xFP16 (+8).  The default 'auto'
+    (= '3xfp16', all kernels) is covered by test_golden_forward."""
     cfg, sd, inp, want, edges = load_golden(case)
     net = make_net(cfg, sd)
     net.math_mode = mode
@@ -55,7 +56,23 @@ def test_tensor_core_mode_rejected_for_other_widths():
     assert net.math_mode == 0
     run(net, inp)
     with pytest.raises(RuntimeError, match='hidden_nf=256'):
-        net.math_mode = 7
+        net.math_mode = '3xfp16'
+
+
+def test_fp16_split_range_overflow_is_reported():
+    """3xFP16 operands overflow beyond |x| ~ 6.5e4: the result turns NaN and the reference's NaN convention fires
+    (ValueError); the range-robust 3xTF32 path handles the same input."""
+    cfg, sd, inp, want, _ = load_golden('config1_n64_l4')
+    big = {k: v.clone() for k, v in sd.items()}
+    big['egnn.embedding.bias'] = big['egnn.embedding.bias'] + 3.0e5      # hidden features far outside the fp16 range
+    net = make_net(cfg, big)
+    with pytest.raises(ValueError, match='NaN detected'):
+        run(net, inp)
+    net.math_mode = '3xtf32'
+    a = run(net, inp)
+    net.math_mode = 'fp32'
+    b = run(net, inp)
+    assert torch.isfinite(a[0]).all() and torch.allclose(a[0], b[0], atol=1e-3, rtol=1e-3)
 
 
 @pytest.mark.parametrize('case', golden_cases())
