@@ -155,16 +155,17 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
   w.rdec2_w = cp("residue_decoder.2.weight"); w.rdec2_b = cp("residue_decoder.2.bias");
   { float* t = pk.alloc((size_t)Din * H); w.emb_wT = pk.T(P("egnn.embedding.weight"), Din, 0, H, Din, t, H, 0); }
   w.emb_b = cp("egnn.embedding.bias");
-  { float* t = pk.alloc((size_t)H * Din); w.out_wT = pk.T(P("egnn.embedding_out.weight"), H, 0, Din, H, t, Din, 0); }
-  w.out_b = cp("egnn.embedding_out.bias");
+  const int Dpad = (Din + 3) & ~3;
+  { float* t = pk.alloc((size_t)H * Dpad); w.out_wT = pk.T(P("egnn.embedding_out.weight"), H, 0, Din, H, t, Dpad, 0); }
+  { float* t = pk.alloc(Dpad); if (!dry) pack_copy_kernel<<<(Din + 255) / 256, 256>>>(t, P("egnn.embedding_out.bias"), Din); w.out_b = t; }
   const float* emb = De > 0 ? P("edge_embedding.weight") : nullptr;
 
-  auto first_layer = [&](const std::string& pre, float* W1dst, int ldd, int dcol, float* b1dst,
+  auto first_layer = [&](const std::string& pre, float* W1dst, int ldd, int dcol_recv, int dcol_send, float* b1dst,
                          const float** wr, const float** wr0, const float** tb) {
     const float* W1 = P(pre + ".weight");
-    pk.T(W1, ld1, 0, H, H, W1dst, ldd, dcol);          // receiver part  (h[row], egnn_new.py:35/99)
-    pk.T(W1, ld1, H, H, H, W1dst, ldd, dcol + H);      // sender part    (h[col])
-    if (!dry) pack_copy_kernel<<<(H + 255) / 256, 256>>>(b1dst + dcol, P(pre + ".bias"), H);
+    pk.T(W1, ld1, 0, H, H, W1dst, ldd, dcol_recv);     // receiver part  (h[row], egnn_new.py:35/99)
+    pk.T(W1, ld1, H, H, H, W1dst, ldd, dcol_send);     // sender part    (h[col])
+    if (!dry) pack_copy_kernel<<<(H + 255) / 256, 256>>>(b1dst + dcol_recv, P(pre + ".bias"), H);
     float* r = pk.alloc(H); pk.T(W1, ld1, 2 * H, H, 1, r, H, 0); *wr = r;
     float* r0 = pk.alloc(H); pk.T(W1, ld1, 2 * H + 1, H, 1, r0, H, 0); *wr0 = r0;
     if (De > 0) {
@@ -182,7 +183,7 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
       const std::string g = b + ".gcl_" + std::to_string(s);
       GclW& G = w.gcl[k][s];
       float* W1 = pk.alloc((size_t)H * 2 * H); float* b1 = pk.alloc(2 * H);
-      first_layer(g + ".edge_mlp.0", W1, 2 * H, 0, b1, &G.wr, &G.wr0, &G.tb);
+      first_layer(g + ".edge_mlp.0", W1, 2 * H, 0, H, b1, &G.wr, &G.wr0, &G.tb);
       G.W1ab = W1; G.b1ab = b1;
       { float* t = pk.alloc((size_t)H * H); G.W2 = pk.T(P(g + ".edge_mlp.2.weight"), H, 0, H, H, t, H, 0); }
       G.b2 = cp(g + ".edge_mlp.2.bias");
@@ -212,7 +213,7 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     const char* names[2] = {".coord_mlp", ".cross_product_mlp"};
     for (int m = 0; m < 2; ++m) {
       if (m < nm) {
-        first_layer(q + names[m] + ".0", W1, nm * 2 * H, m * 2 * H, b1, &Q.wr[m], &Q.wr0[m], &Q.tb[m]);
+        first_layer(q + names[m] + ".0", W1, nm * 2 * H, m * H, nm * H + m * H, b1, &Q.wr[m], &Q.wr0[m], &Q.tb[m]);
         float* t = pk.alloc((size_t)H * H);
         Q.W2[m] = pk.T(P(q + names[m] + ".2.weight"), H, 0, H, H, t, H, 0);
         Q.b2[m] = cp(q + names[m] + ".2.bias");
@@ -227,8 +228,8 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
       Packer::Blk blk[4];
       for (int m = 0; m < nm; ++m) {
         const float* W = P(q + names[m] + ".0.weight");
-        blk[2 * m] = {W, ld1, 0, H, m * 2 * H};
-        blk[2 * m + 1] = {W, ld1, H, H, m * 2 * H + H};
+        blk[2 * m] = {W, ld1, 0, H, m * H};                    // receiver block
+        blk[2 * m + 1] = {W, ld1, H, H, nm * H + m * H};       // sender block
         Packer::Blk b2 = {P(q + names[m] + ".2.weight"), H, 0, H, 0};
         pk.image(&Q.iW2[m], H, H, &b2, 1);
       }
@@ -256,6 +257,7 @@ static Workspace carve(const dsb_config& c, int64_t NL, int64_t NP, int64_t B, i
   ws.velmean = (float4*)take(sizeof(float4) * (B + 1));
   ws.h = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.hT = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
+  ws.hout = (float*)take(sizeof(float) * (size_t)(N + 1) * (((c.joint_nf + (c.condition_time ? 1 : 0)) + 3) & ~3));
   ws.agg = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 4 * H);
   ws.deg = (int32_t*)take(sizeof(int32_t) * (N + 1));
@@ -474,8 +476,8 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
 #define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
   const int mm = (H == 256) ? dyn->math_mode : 0;
   const bool f16 = (mm & 8) != 0;
-  auto gemm = [&](const GemmArgs& ga, const TcImage& img) -> int {
-    return ((mm & 1) && img.t_hi) ? launch_tc_node_gemm(dyn, ga, img, f16, status, s) : launch_node_gemm(ga, s);
+  auto gemm = [&](const GemmArgs& ga, const TcImage& img, int n_tile_off = 0) -> int {
+    return ((mm & 1) && img.t_hi) ? launch_tc_node_gemm(dyn, ga, img, n_tile_off, f16, status, s) : launch_node_gemm(ga, s);
   };
 
   mark(KC_SETUP);
@@ -485,37 +487,56 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   const float4* xcur = ws.xbuf[0];
   if (nm == 2) { mark(KC_COORD_FINISH); DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, nullptr, false, s)); launches += 1; }
 
+  // the aggregates are zeroed once here; afterwards each consumer re-arms them (node GEMM g3 zeroes agg, coord_finish zeroes xagg)
+  mark(KC_MEMSET);
+  DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
+  DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
+  memsets += 2;
   for (int l = 0; l < c.n_layers; ++l) {
     for (int sub = 0; sub < c.inv_sublayers; ++sub) {
       const GclW& G = dyn->w.gcl[l][sub];
       mark(KC_NODE_GEMM);
-      GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0};
+      GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0, nullptr, 0};
       DSB_TRY(gemm(g1, G.iW1ab));
-      mark(KC_MEMSET);
-      DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
       mark(KC_EDGE_GCL);
       DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
-      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1};
+      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1, nullptr, 0};
       DSB_TRY(gemm(g2, G.iW3));
-      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0};
+      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0, ws.agg, H};
       DSB_TRY(gemm(g3, G.iW4));
-      launches += 4; memsets += 1;
+      launches += 4;
     }
     const EquivW& Q = dyn->w.eq[l];
     mark(KC_NODE_GEMM);
-    GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, nm * 2 * H, Q.b1, nullptr, 0, ws.P, nm * 2 * H, dm.N, nm * 2 * H, 0};
-    DSB_TRY(gemm(g4, Q.iW1));
-    mark(KC_MEMSET);
-    DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
+    const int ldq = nm * 2 * H, nrecv = nm * H;
+    if (dm.n_coord_rows < dm.N) {
+      // conditional mode: the receiver-side first layer is needed only for rows whose coordinates move (ligand rows)
+      GemmArgs g4a = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, ldq, Q.b1, nullptr, 0, ws.P, ldq, dm.n_coord_rows, nrecv, 0, nullptr, 0};
+      DSB_TRY(gemm(g4a, Q.iW1, 0));
+      GemmArgs g4b = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1 + nrecv, ldq, Q.b1 + nrecv, nullptr, 0, ws.P + nrecv, ldq, dm.N, nrecv, 0, nullptr, 0};
+      DSB_TRY(gemm(g4b, Q.iW1, nrecv / 256));
+      launches += 1;
+    } else {
+      GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, ldq, Q.b1, nullptr, 0, ws.P, ldq, dm.N, ldq, 0, nullptr, 0};
+      DSB_TRY(gemm(g4, Q.iW1));
+    }
     mark(KC_EDGE_COORD);
     DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, f16, status, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];
     mark(KC_COORD_FINISH);
     DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
     xcur = xnext;
-    launches += 3; memsets += 1;
+    launches += 3;
+  }
+  // embedding_out as a node GEMM (H -> Din, zero-padded to a multiple of 4 columns), decoders in post_kernel
+  mark(KC_NODE_GEMM);
+  {
+    const int Din = c.joint_nf + (c.condition_time ? 1 : 0), Dpad = (Din + 3) & ~3;
+    GemmArgs go = {ws.h, H, H, nullptr, 0, 0, 1.f, dyn->w.out_wT, Dpad, dyn->w.out_b, nullptr, 0, ws.hout, Dpad, dm.N, Dpad, 0, nullptr, 0};
+    DSB_TRY(launch_node_gemm(go, s));
+    launches += 1;
   }
   mark(KC_POST);
   DSB_TRY(launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s));

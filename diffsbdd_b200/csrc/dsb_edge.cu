@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(ETHREADS, 1) edge_gcl_kernel(EdgeGclArgs a) {
 
 // =====================================================================================================
 struct EdgeCoordArgs {
-  const float* P; int ldp;           // [N][nm*2H]
+  const float* P; int ldp;           // [N][nm*2H]: receiver block (m*H) then sender block (nm*H + m*H)
   const float4* x; const float4* cent; const int32_t* gid;
   const int32_t* row_ptr; int n_rows;   // edges [0, row_ptr[n_rows]) have a moving receiver
   const int32_t *erow, *ecol; const float* ed0; int NL;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(ETHREADS, 1) edge_coord_kernel(EdgeCoordArgs a
     for (int m = 0; m < a.nm; ++m) {
       float acc[8][H / 16];
       const float* v = s_vec + m * 6 * H;
-      edge_mlp_mainloop<H>(acc, Xs, Ws, a.P, a.ldp, m * 2 * H, m * 2 * H + H, v, v + H,
+      edge_mlp_mainloop<H>(acc, Xs, Ws, a.P, a.ldp, m * H, a.nm * H + m * H, v, v + H,
                            has_tb ? v + 3 * H : nullptr, s_row, s_col, s_d2, s_d0,
                            has_tb ? s_type : nullptr, a.w.W2[m]);
       const float* b2 = v + 2 * H;

@@ -41,8 +41,8 @@ struct GclW {            // one GCL (reference egnn_new.py:6-66)
 };
 
 struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); index 0 = coord_mlp, 1 = cross_product_mlp
-  const float* W1;       // [H][nm*2H] (coord recv | coord send | cross recv | cross send)
-  const float* b1;       // [nm*2H]    (bias | 0 | bias | 0)
+  const float* W1;       // [H][nm*2H] receiver block (coord recv | cross recv) then sender block (coord send | cross send)
+  const float* b1;       // [nm*2H]    (bias coord | bias cross | 0 | 0)
   const float* wr[2];
   const float* wr0[2];
   const float* tb[2];
@@ -60,7 +60,7 @@ struct PackedWeights {
   const float *adec0_w, *adec0_b, *adec2_w, *adec2_b;
   const float *rdec0_w, *rdec0_b, *rdec2_w, *rdec2_b;
   const float *emb_wT, *emb_b;      // [Din][H] k-major, [H]
-  const float *out_wT, *out_b;      // [H][Din] k-major, [Din]
+  const float *out_wT, *out_b;      // [H][Dpad] k-major zero-padded to Dpad = round_up(Din, 4), [Dpad]
   GclW gcl[kMaxLayers][kMaxSub];
   EquivW eq[kMaxLayers];
 };
@@ -74,6 +74,7 @@ struct Workspace {
   float4 *xagg;                 // [N] raw segment sums of trans
   float4 *velmean;              // [B]
   float *h, *hT, *agg, *P;      // [N][H], [N][H], [N][H], [N][4H]
+  float *hout;                  // [N][Dpad] embedding_out result
   int32_t *deg, *row_ptr;       // [N], [N+1]
   int32_t *erow, *ecol;         // [Ecap]
   float *ed0;                   // [Ecap]
@@ -135,6 +136,7 @@ struct GemmArgs {
   const float* R; int ldr;                          // residual (added after bias) or nullptr
   float* C; int ldc;
   int M; int Nn; int act;                           // act: 0 none, 1 SiLU
+  float* Z; int ldz;                                // optional: Z[m][n] = 0 for every output element (re-arms the aggregate)
 };
 int launch_node_gemm(const GemmArgs& a, cudaStream_t s);
 
@@ -161,7 +163,8 @@ void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int sc
 void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale);
 void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsigned* out);
 int configure_tc_kernels();
-int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, bool f16, int32_t* status, cudaStream_t s);
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, int n_tile_off, bool f16, int32_t* status,
+                        cudaStream_t s);
 int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, bool f16,
                        int32_t* status, cudaStream_t s);
 int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, bool f16,

@@ -253,7 +253,7 @@ int launch_edges(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, int
 // (egnn_new.py:307-310).  One CTA per graph.
 // =====================================================================================================
 __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restrict__ x_old, float4* __restrict__ x_new,
-                                                            const float4* __restrict__ xagg, const int32_t* __restrict__ lig_off,
+                                                            float4* __restrict__ xagg, const int32_t* __restrict__ lig_off,
                                                             const int32_t* __restrict__ poc_off, int NL, int n_coord_rows,
                                                             float norm, int apply_update, float4* __restrict__ cent) {
   const int g = blockIdx.x;
@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restr
     if (apply_update) {
       if (i < n_coord_rows) {
         const float4 a = xagg[i];
+        xagg[i] = make_float4(0.f, 0.f, 0.f, 0.f);      // re-arm the accumulator for the next block
         v.x = v.x + __fdiv_rn(a.x, norm);
         v.y = v.y + __fdiv_rn(a.y, norm);
         v.z = v.z + __fdiv_rn(a.z, norm);
@@ -337,9 +338,8 @@ __global__ void __launch_bounds__(128) velmean_kernel(const float4* __restrict__
 }
 
 struct PostArgs {
-  const float* h; const float4* x_fin; const float4* x_in; const int32_t* gid; const float4* velmean;
+  const float* hout; int Dpad; const float4* x_fin; const float4* x_in; const int32_t* gid; const float4* velmean;
   int NL, NP, A, R, J, Din, H; int joint;
-  const float *out_wT, *out_b;
   const float *adec0_w, *adec0_b, *adec2_w, *adec2_b, *rdec0_w, *rdec0_b, *rdec2_w, *rdec2_b;
   float* out_atoms; float* out_res; int32_t* status;
 };
@@ -357,12 +357,14 @@ __global__ void __launch_bounds__(PREP_THREADS) post_kernel(PostArgs p) {
   const int ld = 3 + F;
   const float *w0 = is_lig ? p.adec0_w : p.rdec0_w, *b0 = is_lig ? p.adec0_b : p.rdec0_b;
   const float *w2 = is_lig ? p.adec2_w : p.rdec2_w, *b2 = is_lig ? p.adec2_b : p.rdec2_b;
-  float* s_h = sm;                             // [16][H]
-  float* s_o = s_h + PREP_NODES * p.H;         // [16][J]
+  float* s_o = sm;                             // [16][J]  embedding_out result, time channel dropped (dynamics.py:149)
   float* s_hid = s_o + PREP_NODES * p.J;       // [16][2F]
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < nn * p.H; i += PREP_THREADS) s_h[i] = p.h[(size_t)node0 * p.H + i];
+  for (int i = tid; i < nn * p.J; i += PREP_THREADS) {
+    const int n = i / p.J, o = i - n * p.J;
+    s_o[i] = p.hout[(size_t)(node0 + n) * p.Dpad + o];
+  }
   for (int i = tid; i < nn; i += PREP_THREADS) {
     const float4 a = p.x_fin[node0 + i], b = p.x_in[node0 + i];
     float vx = a.x - b.x, vy = a.y - b.y, vz = a.z - b.z;
@@ -373,20 +375,6 @@ __global__ void __launch_bounds__(PREP_THREADS) post_kernel(PostArgs p) {
     }
     float* row = out + (size_t)(base + i) * ld;
     row[0] = vx; row[1] = vy; row[2] = vz;
-  }
-  __syncthreads();
-  for (int o = tid; o < p.J; o += PREP_THREADS) {     // time channel (row J of embedding_out) is sliced off (dynamics.py:149)
-    float acc[PREP_NODES];
-    const float bias = p.out_b[o];
-#pragma unroll
-    for (int n = 0; n < PREP_NODES; ++n) acc[n] = bias;
-    for (int k = 0; k < p.H; ++k) {
-      const float w = p.out_wT[(size_t)k * p.Din + o];
-#pragma unroll
-      for (int n = 0; n < PREP_NODES; ++n) acc[n] = fmaf(s_h[n * p.H + k], w, acc[n]);
-    }
-#pragma unroll
-    for (int n = 0; n < PREP_NODES; ++n) s_o[n * p.J + o] = acc[n];
   }
   __syncthreads();
   for (int i = tid; i < nn * F2; i += PREP_THREADS) {
@@ -412,15 +400,14 @@ int launch_post(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, cons
     velmean_kernel<<<dm.B, 128, 0, s>>>(x_final, ws.xbuf[0], ws.lig_off, ws.poc_off, dm.NL, ws.velmean);
   }
   PostArgs p;
-  p.h = ws.h; p.x_fin = x_final; p.x_in = ws.xbuf[0]; p.gid = ws.gid; p.velmean = ws.velmean;
+  p.hout = ws.hout; p.Dpad = ((c.joint_nf + (c.condition_time ? 1 : 0)) + 3) & ~3; p.x_fin = x_final; p.x_in = ws.xbuf[0]; p.gid = ws.gid; p.velmean = ws.velmean;
   p.NL = dm.NL; p.NP = dm.NP; p.A = c.atom_nf; p.R = c.residue_nf; p.J = c.joint_nf;
   p.Din = c.joint_nf + (c.condition_time ? 1 : 0); p.H = c.hidden_nf; p.joint = c.update_pocket_coords;
-  p.out_wT = w.out_wT; p.out_b = w.out_b;
   p.adec0_w = w.adec0_w; p.adec0_b = w.adec0_b; p.adec2_w = w.adec2_w; p.adec2_b = w.adec2_b;
   p.rdec0_w = w.rdec0_w; p.rdec0_b = w.rdec0_b; p.rdec2_w = w.rdec2_w; p.rdec2_b = w.rdec2_b;
   p.out_atoms = out_atoms; p.out_res = out_residues; p.status = status;
   int Fm = c.atom_nf > c.residue_nf ? c.atom_nf : c.residue_nf;
-  size_t smem = sizeof(float) * PREP_NODES * (size_t)(p.H + p.J + 2 * Fm);
+  size_t smem = sizeof(float) * PREP_NODES * (size_t)(p.J + 2 * Fm);
   int blocks = (dm.NL + PREP_NODES - 1) / PREP_NODES + (dm.NP + PREP_NODES - 1) / PREP_NODES;
   if (blocks == 0) return 0;
   post_kernel<<<blocks, PREP_THREADS, smem, s>>>(p);
@@ -541,6 +528,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) node_gemm_kernel(GemmArgs g) {
         v[0] = r.x + v[0]; v[1] = r.y + v[1]; v[2] = r.z + v[2]; v[3] = r.w + v[3];
       }
       *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+      if (g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)m * g.ldz + n) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }

@@ -136,6 +136,7 @@ struct TcGemmArgs {
   const float* Bhi; const float* Blo;        // [Nn/256][K/32][8192]
   const float* bias; const float* R; int ldr;
   float* C; int ldc; int M; int Nn; int act;
+  float* Z; int ldz;
   float inv_scale;                             // 3xFP16: 1 / (X_SCALE * weight scale); 1 for 3xTF32
   int32_t* status;
 };
@@ -196,6 +197,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(cc + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          if (g.Z) {
+            float* zz = g.Z + (size_t)row * g.ldz + n;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(zz + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
       tc_fence_before();
@@ -203,36 +209,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       if (lane == 0) mbar_arrive(&ctl->epi_done[a]);
     }
   } else if (warp < MMA_WARP) {
+    // same coalesced mapping as the edge kernels: warp pw owns rows [16 pw, 16 pw + 16), lane = (sub-row, 16-byte piece)
     const int ptid = threadIdx.x - EPI_WARPS * 32;
-    const int pr = ptid >> 1, phf = ptid & 1;
+    const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
     uint32_t gc = 0;
-    auto load_half = [&](int m, bool valid, int hf, float4 (&v)[4]) {
-      const int k = hf * TKC + phf * 16;
+    auto load_half = [&](int m0, int hf, float4 (&v)[4]) {
+      const int k = hf * TKC + 4 * pc;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 16 * pw + 4 * i + sr;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
+        if (m < g.M) {
           if (k < g.K1) {
-            x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k + 4 * q);
+            x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k);
           } else {
-            x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1) + 4 * q);
+            x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1));
             if (g.div2 != 1.0f) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
           }
         }
-        v[q] = x;
+        v[i] = x;
       }
     };
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      const int m = (tile / ntn) * TM + pr;
-      const bool valid = m < g.M;
+      const int m0 = (tile / ntn) * TM;
       float4 cur[4], nxt[4];
-      load_half(m, valid, 0, cur);
+      load_half(m0, 0, cur);
       for (int hf = 0; hf < halves; ++hf) {
-        if (hf + 1 < halves) load_half(m, valid, hf + 1, nxt);
+        if (hf + 1 < halves) load_half(m0, hf + 1, nxt);
         const int s = gc & 1;
         if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-        store_row16<F16>(cv.stages + (size_t)s * STAGE_BYTES, pr, hf, phf, cur);
+        char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, hf, pc, cur[i]);
         if (!F16 || (hf & 1)) {
           fence_proxy_async();
           __syncwarp();
@@ -293,6 +302,12 @@ struct TcEdgeArgs {
   float inv_scale[2];                        // 3xFP16: 1 / (X_SCALE * W2 scale) per MLP; 1 for 3xTF32
   int32_t* status;
 };
+
+// one RED per (receiver segment, column): kept out of line so the unrolled row loop only carries a branch
+__device__ __noinline__ void red_flush(float* dst, int myrow, int src_lane, float sum, int dbg) {
+  const int prow = __shfl_sync(0xffffffffu, myrow, src_lane);
+  if (prow >= 0 && !(dbg & 64)) atomicAdd(dst + (size_t)prow * H256, sum);
+}
 
 // per-edge scalars of tile `e0`, written by the 128 even producer threads
 template <bool COORD>
@@ -411,19 +426,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * EPI_T_STRIDE + j] = v[j] * gate;
           __syncwarp();
+          // all 32 rows of this lane's column into registers first (independent LDS), then the in-order segment sums
+          float t[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) t[rr] = T[rr * EPI_T_STRIDE + lane];
           float* dst = a.agg + cb * 32 + lane;
-          unsigned rest = seg_start;
-#pragma unroll 1
-          while (rest) {                       // one iteration per receiver segment (warp-uniform control flow)
-            const int r0 = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const int r1 = rest ? __ffs(rest) - 1 : 32;
-            const int prow = __shfl_sync(0xffffffffu, myrow, r0);
-            float sum = 0.f;
-#pragma unroll 4
-            for (int rr = r0; rr < r1; ++rr) sum += T[rr * EPI_T_STRIDE + lane];
-            if (prow >= 0 && !(edbg & 64)) atomicAdd(dst + (size_t)prow * H256, sum);
+          float sum = t[0];
+#pragma unroll
+          for (int rr = 1; rr < 32; ++rr) {
+            if ((seg_start >> rr) & 1u) {            // warp-uniform, rare (1-3 segments per 32 rows): real branch
+              red_flush(dst, myrow, rr - 1, sum, edbg);
+              sum = 0.f;
+            }
+            sum += t[rr];
           }
+          red_flush(dst, myrow, 31, sum, edbg);
           __syncwarp();
         }
       } else {
@@ -472,62 +489,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
     }
   } else if (warp < MMA_WARP) {
     // ------------------------------------------------------------------------------------------ producers
+    // Thread mapping (coalesced gathers): producer warp pw owns tile rows [16 pw, 16 pw + 16); lane = (sub-row sr, piece p):
+    // 8 lanes cover one row's contiguous 128 bytes (32 k-values), one LDG.128 instruction covers 4 rows = 4 L1 wavefronts
+    // (the former 2-threads-per-row mapping touched 16 rows per instruction).  A thread handles 4 rows x 4 k per 32-k half.
     const int ptid = threadIdx.x - EPI_WARPS * 32;
-    const int pr = ptid >> 1, phf = ptid & 1;
+    const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
     const int dbg = g_tc_debug;
     uint32_t gc = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       const int par = it & 1;
       const int e0 = (blockIdx.x + it * gridDim.x) * TM;
       mbar_wait(&ctl->scal_empty[par], ((it >> 1) & 1) ^ 1);   // epilogue finished the tile that last used these buffers
-      if (phf == 0) edge_scalars<COORD>(a, ex, par, pr, e0, E);
+      if (ptid < TM) edge_scalars<COORD>(a, ex, par, ptid, e0, E);
       producers_sync();
       if (ptid == 0) mbar_arrive(&ctl->scal_full[par]);
-      const int prow = ex->row[par][pr] < 0 ? 0 : ex->row[par][pr];
-      const int pcol = ex->col[par][pr];
-      const float pd2 = ex->d2[par][pr], pd0 = ex->d0[par][pr];
-      const int ptype = ex->type[par][pr];
+      int trow[4]; float pd2[4], pd0[4];
+      const float* Pa[4]; const float* Pb[4]; const float* tbp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 16 * pw + 4 * i + sr;
+        trow[i] = r;
+        const int prow = ex->row[par][r] < 0 ? 0 : ex->row[par][r];
+        Pa[i] = a.P + (size_t)prow * a.ldp + 4 * pc;                                  // receiver block (+ m*H per MLP)
+        Pb[i] = a.P + (size_t)ex->col[par][r] * a.ldp + nm * H256 + 4 * pc;           // sender block
+        pd2[i] = ex->d2[par][r]; pd0[i] = ex->d0[par][r];
+        tbp[i] = has_tb ? a.tb[0] + ex->type[par][r] * H256 + 4 * pc : nullptr;
+      }
       for (int m = 0; m < nm; ++m) {
-        const float* Pa = a.P + (size_t)prow * a.ldp + m * 2 * H256 + phf * 16;
-        const float* Pb = a.P + (size_t)pcol * a.ldp + m * 2 * H256 + H256 + phf * 16;
-        const float* wr = ex->vec[m] + phf * 16; const float* wr0 = wr + H256;
-        const float* tb = has_tb ? a.tb[m] + ptype * H256 + phf * 16 : nullptr;
+        const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H256;
+        const size_t tb_off = has_tb ? (size_t)(a.tb[m] - a.tb[0]) : 0;
         float4 ga[4], gb[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          ga[q] = *reinterpret_cast<const float4*>(Pa + 4 * q);
-          gb[q] = *reinterpret_cast<const float4*>(Pb + 4 * q);
+        for (int i = 0; i < 4; ++i) {
+          ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256);
+          gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256);
         }
 #pragma unroll 1
         for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
           float4 v[4];
           if (dbg & 2) { v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
-          else
+          else {
+            const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
+            const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int k0 = hf * TKC + 4 * q;
-            const float4 r4 = *reinterpret_cast<const float4*>(wr + k0);
-            const float4 r04 = *reinterpret_cast<const float4*>(wr0 + k0);
-            float u0 = fmaf(pd0, r04.x, fmaf(pd2, r4.x, ga[q].x + gb[q].x));
-            float u1 = fmaf(pd0, r04.y, fmaf(pd2, r4.y, ga[q].y + gb[q].y));
-            float u2 = fmaf(pd0, r04.z, fmaf(pd2, r4.z, ga[q].z + gb[q].z));
-            float u3 = fmaf(pd0, r04.w, fmaf(pd2, r4.w, ga[q].w + gb[q].w));
-            if (has_tb) {
-              const float4 t4 = *reinterpret_cast<const float4*>(tb + k0);
-              u0 += t4.x; u1 += t4.y; u2 += t4.z; u3 += t4.w;
+            for (int i = 0; i < 4; ++i) {
+              float u0 = fmaf(pd0[i], r04.x, fmaf(pd2[i], r4.x, ga[i].x + gb[i].x));
+              float u1 = fmaf(pd0[i], r04.y, fmaf(pd2[i], r4.y, ga[i].y + gb[i].y));
+              float u2 = fmaf(pd0[i], r04.z, fmaf(pd2[i], r4.z, ga[i].z + gb[i].z));
+              float u3 = fmaf(pd0[i], r04.w, fmaf(pd2[i], r4.w, ga[i].w + gb[i].w));
+              if (has_tb) {
+                const float4 t4 = *reinterpret_cast<const float4*>(tbp[i] + tb_off + hf * TKC);
+                u0 += t4.x; u1 += t4.y; u2 += t4.z; u3 += t4.w;
+              }
+              v[i] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
             }
-            v[q] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
           }
           if (hf + 1 < halves && !(dbg & (2 | 128))) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              ga[q] = *reinterpret_cast<const float4*>(Pa + (hf + 1) * TKC + 4 * q);
-              gb[q] = *reinterpret_cast<const float4*>(Pb + (hf + 1) * TKC + 4 * q);
+            for (int i = 0; i < 4; ++i) {
+              ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256 + (hf + 1) * TKC);
+              gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
             }
           }
           if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-          if (!(dbg & (2 | 256))) store_row16<F16>(cv.stages + (size_t)s * STAGE_BYTES, pr, hf, phf, v);
+          if (!(dbg & (2 | 256))) {
+            char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) store_piece<F16>(st, trow[i], hf, pc, v[i]);
+          }
           if (!F16 || (hf & 1)) {
             fence_proxy_async();
             __syncwarp();
@@ -569,7 +599,8 @@ int configure_tc_kernels() {
   return 0;
 }
 
-int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, bool f16, int32_t* status, cudaStream_t s) {
+int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, int n_tile_off, bool f16, int32_t* status,
+                        cudaStream_t s) {
   if (g.M == 0) return 0;
   const int K = g.K1 + g.K2;
   if ((g.Nn % TN) || (K % TKC16) || (g.K1 % TKC16) || (g.lda1 % 4) || (g.ldc % 4)) {
@@ -578,7 +609,9 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   }
   TcGemmArgs a;
   a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2;
-  a.Bhi = f16 ? w.h_hi : w.t_hi; a.Blo = f16 ? w.h_lo : w.t_lo;
+  const size_t img_off = (size_t)n_tile_off * (K / (f16 ? TKC16 : TKC)) * B_CHUNK_FLOATS;     // skip the first n-tiles of the image
+  a.Bhi = (f16 ? w.h_hi : w.t_hi) + img_off; a.Blo = (f16 ? w.h_lo : w.t_lo) + img_off;
+  a.Z = g.Z; a.ldz = g.ldz;
   a.bias = g.bias; a.R = g.R; a.ldr = g.ldr; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.Nn = g.Nn; a.act = g.act;
   a.inv_scale = f16 ? w.h_inv : 1.0f; a.status = status;
   const int n_tiles = (g.Nn / TN) * ((g.M + TM - 1) / TM);

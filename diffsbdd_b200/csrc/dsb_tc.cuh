@@ -214,20 +214,25 @@ __device__ __forceinline__ void store_split_f16(char* a_hi, char* a_lo, int row,
   *reinterpret_cast<uint4*>(a_lo + off) = lv;
 }
 
-// Producer-side store of 16 consecutive k-values of one row (k = half*32 + phf*16 + 0..15 of the tile's K range).
-//   TF32: chunk (stage) = one 32-k half; four 16-byte stores per operand at chunk positions phf*4 + q
-//   FP16: chunk (stage) = two halves (64 k); two 16-byte stores per operand at positions (half&1)*4 + phf*2 + j
+// Producer-side store of 4 consecutive k-values (piece p = k/4 of the 32-k half `half`) of one tile row.
+//   TF32: chunk (stage) = one 32-k half: 16-byte stores at chunk position p
+//   FP16: chunk (stage) = two halves (64 k): 8-byte stores at byte (half&1)*64 + 8p of the row
+// An FP16 activation beyond the fp16 range becomes inf here and reaches the output as NaN -> the NaN guard of the
+// denoiser raises (dynamics.py:155-159 convention); 3xTF32 has no such limit.
 template <bool F16>
-__device__ __forceinline__ void store_row16(char* st, int row, int half, int phf, const float4 (&v)[4]) {
+__device__ __forceinline__ void store_piece(char* st, int row, int half, int p, float4 v) {
   if constexpr (F16) {
-    // An activation beyond the fp16 range becomes inf here and reaches the output as NaN -> the NaN guard of the
-    // denoiser raises (dynamics.py:155-159 convention); 3xTF32 has no such limit.
-    const int c0 = (half & 1) * 4 + phf * 2;
-    store_split_f16(st, st + A_CHUNK_BYTES, row, c0, v[0], v[1]);
-    store_split_f16(st, st + A_CHUNK_BYTES, row, c0 + 1, v[2], v[3]);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    const uint32_t off = sw128_offset(row, (half & 1) * 4 + (p >> 1)) + (p & 1) * 8;
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(st + off) = hv;
+    *reinterpret_cast<uint2*>(st + A_CHUNK_BYTES + off) = lv;
   } else {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) store_split(st, st + A_CHUNK_BYTES, row, phf * 4 + q, v[q]);
+    store_split(st, st + A_CHUNK_BYTES, row, p, v);
   }
 }
 
