@@ -338,6 +338,12 @@ def run_b200(args):
             N, H, L, S = B * (NL + NP), cfg.hidden_nf, cfg.n_layers, cfg.inv_sublayers
             n_gcl = args.profile_calls * L * S
             gcl_ms = prof['edge_gcl']['ms'] / max(1, n_gcl)
+            mode = dyn.math_mode
+            tensor_path = bool(mode & 2)
+            split = '3xfp16' if (mode & 8) else '3xtf32'
+            kname = (f'tc_edge_kernel<gcl,{split}>' if tensor_path else f'edge_gcl_kernel<{H}>')
+            # algorithmic work of ONE launch of the dominant kernel: all E edges through the factorised first layer
+            # (+SiLU), the HxH second layer, SiLU, attention gate and the receiver segment sum
             alg_bytes = N * 2 * H * 4 + N * H * 4 + E * 12 + N * 16 + (H * H + 7 * H) * 4
             alg_flops = E * (2 * H * H + 12 * H)
             peaks = {}
@@ -347,27 +353,37 @@ def run_b200(args):
             except Exception:
                 pass
             hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-            peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else '6.65 TB/s (of fallback)'
-            ach = alg_bytes / (gcl_ms * 1e-3) / 1e9
+            tens_peak = float(peaks.get('bf16_tflops', 1590.0))
+            src = 'MEASURED_PEAKS.json (of measured)' if peaks else 'B200_PROFILING.md fallback (of fallback)'
             traffic, traffic_src = None, None
             try:   # DRAM bytes per launch from the committed ncu --set full capture (never measured under the profiler here)
                 with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
-                    tr = json.load(f).get(f'edge_gcl_kernel<{H}>')
+                    tr = json.load(f).get(kname)
                 if tr:
                     traffic, traffic_src = tr['dram_bytes_per_launch'], tr['source']
             except Exception:
                 pass
-            roof = {'bound': 'hbm', 'kernel': f'edge_gcl_kernel<{H}>', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': ach / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src,
-                    'algorithmic_bytes_per_launch': alg_bytes,
-                    'avg_launch_ms': gcl_ms, 'edges': E, 'peak_source': peak_src,
-                    'note': 'kernel is FP32-FMA bound by construction at hidden_nf=256 (SURVEY.md §8(d)); see roofline_fp32'}
+            ach_b = alg_bytes / (gcl_ms * 1e-3) / 1e9
+            ach_f = alg_flops / (gcl_ms * 1e-3) / 1e12
             smax = (clocks.get('sm_max_mhz') or 1965.0)
             fp32_peak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * 2 * smax * 1e6 / 1e12
-            ach32 = alg_flops / (gcl_ms * 1e-3) / 1e12
-            roof32 = {'bound': 'fp32_simt', 'kernel': 'edge_gcl_kernel<256>', 'achieved': ach32, 'peak': fp32_peak,
-                      'unit': 'TFLOP/s', 'frac': ach32 / fp32_peak, 'algorithmic_flops_per_launch': alg_flops,
-                      'peak_source': f'SMs x 128 FMA x 2 x clocks.max.sm ({smax:.0f} MHz), nominal'}
+            common = {'kernel': kname, 'avg_launch_ms': gcl_ms, 'edges': E, 'traffic': traffic, 'traffic_source': traffic_src,
+                      'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_flops_per_launch': alg_flops}
+            if tensor_path:
+                # the contraction runs on the tensor pipe as 3 split products: executed tensor FLOPs = 3 x algorithmic
+                roof = dict(common, bound='tensor', achieved=ach_f, peak=tens_peak, unit='TFLOP/s', frac=ach_f / tens_peak,
+                            executed_tensor_tflops=3 * ach_f, executed_frac=3 * ach_f / tens_peak,
+                            peak_source='bf16_tflops, ' + src,
+                            note=('achieved counts ALGORITHMIC fp32 FLOPs (one product per MAC); the kernel executes 3 half-precision '
+                                  'MMAs per MAC to keep fp32-grade accuracy, so the tensor pipe does 3x this'))
+                roof32 = {'bound': 'hbm', 'kernel': kname, 'achieved': ach_b, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_b / hbm_peak,
+                          'peak_source': 'hbm_gbs, ' + src, 'note': 'HBM fraction as BASELINE.json north_star requests; the path is not HBM-bound'}
+            else:
+                roof = dict(common, bound='hbm', achieved=ach_b, peak=hbm_peak, unit='GB/s', frac=ach_b / hbm_peak,
+                            peak_source='hbm_gbs, ' + src,
+                            note='kernel is FP32-FMA bound by construction at hidden_nf=256 (SURVEY.md §8(d)); see roofline_fp32')
+                roof32 = {'bound': 'fp32_simt', 'kernel': kname, 'achieved': ach_f, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+                          'frac': ach_f / fp32_peak, 'peak_source': f'SMs x 128 FMA x 2 x clocks.max.sm ({smax:.0f} MHz), nominal'}
             tot = sum(v['ms'] for v in prof.values())
             kernel_ms = {k: round(v['ms'] / args.profile_calls, 4) for k, v in prof.items()}
             kernel_ms['total_per_call'] = round(tot / args.profile_calls, 4)
@@ -380,14 +396,14 @@ def run_b200(args):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': workload_name(args, yml), 'global_batch': B * world, 'batch_per_gpu': B,
+                'config': {'workload': workload_name(args, yml), 'arithmetic': {0: 'fp32 FFMA', 7: '3xTF32 tcgen05', 15: '3xFP16 tcgen05'}.get(dyn.math_mode, str(dyn.math_mode)), 'global_batch': B * world, 'batch_per_gpu': B,
                            'n_lig': NL, 'n_pocket': NP, 'timesteps': T, 'denoiser_calls_per_step': T + 1,
                            'edges_last_call': e_last, 'parallelism': f'dp{world} (independent pockets per rank, '
                            'final all_gather of ligands)', 'l2': '256 MiB read+write flush before every timed step',
                            'loop_engine': 'cuda_graph replay of one reverse step' if ddpm._graph_cache else 'eager',
                            'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': gpu_launches,
-                'launches_per_denoiser_call': launches_fwd, 'roofline': roof, 'roofline_fp32': roof32,
+                'launches_per_denoiser_call': launches_fwd, 'math_mode': dyn.math_mode, 'roofline': roof, 'roofline_secondary': roof32,
                 'kernel_ms_per_denoiser_call': kernel_ms, 'cpu_baseline': cpu_base}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -370,6 +370,7 @@ int dsb_dynamics_create(const dsb_config* cfg, const float* const* params, int n
   if (ce != cudaSuccess) { set_error("weight packing failed: %s", cudaGetErrorString(ce)); cudaFree(d->blob); delete d; return DSB_ERR_CUDA; }
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (int e = configure_node_kernels()) { cudaFree(d->blob); delete d; return e; }
   if (int e = configure_edge_kernels(cfg->hidden_nf)) { cudaFree(d->blob); delete d; return e; }
   if (cfg->hidden_nf == 256) { if (int e = configure_tc_kernels()) { cudaFree(d->blob); delete d; return e; } }
   *out = d;

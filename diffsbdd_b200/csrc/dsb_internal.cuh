@@ -139,6 +139,7 @@ struct GemmArgs {
   float* Z; int ldz;                                // optional: Z[m][n] = 0 for every output element (re-arms the aggregate)
 };
 int launch_node_gemm(const GemmArgs& a, cudaStream_t s);
+int configure_node_kernels();
 
 int launch_plan(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const int64_t* mask_atoms,
                 const int64_t* mask_residues, cudaStream_t s);

@@ -533,6 +533,22 @@ __global__ void __launch_bounds__(GTHREADS, 2) node_gemm_kernel(GemmArgs g) {
   }
 }
 
+// All kernels of the library ask for the maximum shared-memory carve-out: the tensor-core kernels need ~225 KB, and an SM
+// that has to switch its L1/shared split between consecutive launches drains first.  The small kernels do not depend on L1.
+int configure_node_kernels() {
+  const int mx = cudaSharedmemCarveoutMaxShared;
+  DSB_CUDA_OK(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_rows_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_rows_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(coord_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(velmean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(post_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  DSB_CUDA_OK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx));
+  return 0;
+}
+
 int launch_node_gemm(const GemmArgs& a, cudaStream_t s) {
   if (a.M == 0) return 0;
   if ((a.K1 % GBK) || (a.K2 % GBK) || (a.Nn % 4) || (a.ldw % 4) || (a.ldc % 4) || (a.lda1 % 4)) {

@@ -80,6 +80,12 @@ void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsig
 extern "C" int dsb_debug_set_tc_flags(int flags) {
   return cudaMemcpyToSymbol(tc::g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -3;
 }
+// reads (and clears) the 32 cycle counters accumulated by kernels run with flag 512
+extern "C" int dsb_debug_read_tc_prof(unsigned long long* out32) {
+  if (cudaMemcpyFromSymbol(out32, tc::g_tc_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return -3;
+  unsigned long long z[32] = {0};
+  return cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z)) == cudaSuccess ? 0 : -3;
+}
 
 // ---- common prologue / epilogue of every TC kernel -----------------------------------------------------------------
 constexpr size_t kControlBytes = 128;      // keeps the per-kernel extras 16-byte aligned for float4 access
@@ -99,6 +105,7 @@ __device__ __forceinline__ Carve carve_smem(uint8_t* raw) {
   return c;
 }
 constexpr size_t kTcSmemBase = 1024 + (size_t)NSTAGE * STAGE_BYTES + kControlBytes;
+constexpr int GEMM_T_STRIDE = 36;          // floats; 16-byte aligned rows, conflict-free for row-wise STS.128 and LDS.128
 
 __device__ __forceinline__ void tc_begin(Control* ctl, int warp) {
   if (threadIdx.x == 0) control_init(ctl);
@@ -152,58 +159,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (n_my == 0) return;
   const int K = g.K1 + g.K2, halves = K / TKC, chunks = F16 ? halves / 2 : halves;
+  const bool gprof = (g_tc_debug & 512) && blockIdx.x == 0;
+  const long long k0 = gprof ? tc_clock() : 0;
   tc_begin(ctl, warp);
+  const long long k1 = gprof ? tc_clock() : 0;
+  if (gprof && threadIdx.x == 0) { atomicAdd(&g_tc_prof[16], (unsigned long long)(k1 - k0)); atomicAdd(&g_tc_prof[23], 1ull); }
 
   if (warp < EPI_WARPS) {
-    const int r = threadIdx.x;
+    // Epilogue.  tcgen05.ld gives each thread one accumulator ROW; storing rows directly would make every
+    // STG.128 / residual LDG.128 touch 32 different rows (32 L1 wavefronts per 512 bytes).  Each 32x32 block is
+    // therefore transposed through a per-warp shared buffer so that 8 lanes cover 128 contiguous bytes of one row
+    // (4 rows = 4 wavefronts per instruction).
+    float* T = reinterpret_cast<float*>(cv.extra) + warp * (32 * GEMM_T_STRIDE);
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int m0 = (tile / ntn) * TM, n0 = (tile % ntn) * TN;
       const int a = it & 1;
+      const long long e0 = gprof ? tc_clock() : 0;
       mbar_wait(&ctl->acc_full[a], (it >> 1) & 1);
       tc_fence_after();
-      const int row = m0 + r;
+      const long long e1 = gprof ? tc_clock() : 0;
+      if (gprof && threadIdx.x == 0) atomicAdd(&g_tc_prof[17], (unsigned long long)(e1 - (it == 0 ? k1 : e0)));   // epilogue waits for the accumulator
       const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * TN);
 #pragma unroll 1
       for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
         tmem_ld32(taddr + cb * 32, v);
-        if (row < g.M) {
-          const int n = n0 + cb * 32;
-          if (F16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= g.inv_scale;
-          }
-          if (g.bias) {
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = n0 + cb * 32 + tc4;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) bias = *reinterpret_cast<const float4*>(g.bias + n);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b = *reinterpret_cast<const float4*>(g.bias + n + 4 * q);
-              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + tr;
+          const int row = m0 + warp * 32 + rl;
+          float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+          if (row < g.M) {
+            if (F16) { x.x *= g.inv_scale; x.y *= g.inv_scale; x.z *= g.inv_scale; x.w *= g.inv_scale; }
+            x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
+            if (g.act == 1) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+            if (g.R) {
+              const float4 rr = *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + n);
+              x.x = rr.x + x.x; x.y = rr.y + x.y; x.z = rr.z + x.z; x.w = rr.w + x.w;
             }
-          }
-          if (g.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-          }
-          if (g.R) {
-            const float* rr = g.R + (size_t)row * g.ldr + n;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 x = *reinterpret_cast<const float4*>(rr + 4 * q);
-              v[4 * q] = x.x + v[4 * q]; v[4 * q + 1] = x.y + v[4 * q + 1]; v[4 * q + 2] = x.z + v[4 * q + 2]; v[4 * q + 3] = x.w + v[4 * q + 3];
-            }
-          }
-          float* cc = g.C + (size_t)row * g.ldc + n;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(cc + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (g.Z) {
-            float* zz = g.Z + (size_t)row * g.ldz + n;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(zz + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = x;
+            if (g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)row * g.ldz + n) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        __syncwarp();
       }
+      if (gprof && threadIdx.x == 0) atomicAdd(&g_tc_prof[18], (unsigned long long)(tc_clock() - e1));             // epilogue work of one tile
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->epi_done[a]);
@@ -230,6 +239,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
         v[i] = x;
       }
     };
+    const long long p0 = gprof ? tc_clock() : 0;
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int m0 = (tile / ntn) * TM;
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
         for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
       }
     }
+    if (gprof && ptid == 0) atomicAdd(&g_tc_prof[19], (unsigned long long)(tc_clock() - p0));    // producers: all tiles of this CTA
   } else if (warp == MMA_WARP) {
     if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
     __syncwarp();
@@ -266,7 +277,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     }
     __syncwarp();
   }
+  const long long k2 = gprof ? tc_clock() : 0;
   tc_end(ctl, warp);
+  if (gprof && threadIdx.x == 0) {
+    atomicAdd(&g_tc_prof[20], (unsigned long long)(k2 - k1));            // thread 0 (epilogue warp 0): begin -> before teardown
+    atomicAdd(&g_tc_prof[21], (unsigned long long)(tc_clock() - k2));    // teardown (syncthreads + TMEM dealloc)
+    atomicAdd(&g_tc_prof[22], (unsigned long long)n_my);
+  }
 }
 
 // =====================================================================================================
@@ -376,9 +393,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
     for (int vt = 0; vt < n_my; ++vt) {
       const int it = vt / nm, m = vt - it * nm;
       const int par = it & 1, acc = vt & 1;
+      const bool prof_on = (g_tc_debug & 512) && warp == 0 && lane == 0;
+      long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      if (prof_on) c0 = tc_clock();
       if (m == 0) mbar_wait(&ctl->scal_full[par], (it >> 1) & 1);
       mbar_wait(&ctl->acc_full[acc], (vt >> 1) & 1);
       tc_fence_after();
+      if (prof_on) c1 = tc_clock();
       const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TN);
       const float* b2 = ex->vec[m] + 2 * H256;
       const float inv = a.inv_scale[m];
@@ -391,10 +412,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
       float s = 0.f;
       const int edbg = g_tc_debug;
+      long long ld_cyc = 0;
 #pragma unroll 1
       for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
+        const long long l0 = prof_on ? tc_clock() : 0;
         tmem_ld32(taddr + cb * 32, v);
+        if (prof_on) ld_cyc += tc_clock() - l0;
         if (!(edbg & 32))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -411,6 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
         }
         if (!COORD) tmem_st32(taddr + cb * 32, v);
       }
+      if (prof_on) { c2 = tc_clock(); atomicAdd(&g_tc_prof[4], (unsigned long long)ld_cyc); }
       if (!COORD) {
         tmem_wait_st();
         const float gate = has_att ? sigmoid_f(s + ba) : 1.0f;
@@ -422,10 +447,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
 #pragma unroll 1
         for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
+          const long long l0 = prof_on ? tc_clock() : 0;
           tmem_ld32(taddr + cb * 32, v);
+          const long long l1 = prof_on ? tc_clock() : 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * EPI_T_STRIDE + j] = v[j] * gate;
           __syncwarp();
+          if (prof_on) { atomicAdd(&g_tc_prof[5], (unsigned long long)(l1 - l0)); atomicAdd(&g_tc_prof[6], (unsigned long long)(tc_clock() - l1)); }
           // all 32 rows of this lane's column into registers first (independent LDS), then the in-order segment sums
           float t[32];
 #pragma unroll
@@ -480,6 +508,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
           __syncwarp();
         }
       }
+      if (prof_on) {
+        c3 = tc_clock();
+        atomicAdd(&g_tc_prof[0], (unsigned long long)(c1 - c0));   // epilogue: waiting for scalars/accumulator
+        atomicAdd(&g_tc_prof[1], (unsigned long long)(c2 - c1));   // pass 1
+        atomicAdd(&g_tc_prof[2], (unsigned long long)(c3 - c2));   // pass 2 (GCL) / trans+segment sum (coord)
+        atomicAdd(&g_tc_prof[3], 1ull);                            // virtual tiles
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -499,6 +534,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
     for (int it = 0; it < n_my_tiles; ++it) {
       const int par = it & 1;
       const int e0 = (blockIdx.x + it * gridDim.x) * TM;
+      const bool pprof = (dbg & 512) && ptid == 0;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc_wait = 0, acc_store = 0, acc_comp = 0, acc_fence = 0;
+      if (pprof) t0 = tc_clock();
       mbar_wait(&ctl->scal_empty[par], ((it >> 1) & 1) ^ 1);   // epilogue finished the tile that last used these buffers
       if (ptid < TM) edge_scalars<COORD>(a, ex, par, ptid, e0, E);
       producers_sync();
@@ -524,10 +562,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
           ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256);
           gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256);
         }
+        if (pprof && m == 0) { t1 = tc_clock(); atomicAdd(&g_tc_prof[8], (unsigned long long)(t1 - t0)); }   // tile start: scalars + first gathers issued
 #pragma unroll 1
         for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
           float4 v[4];
+          if (pprof) t0 = tc_clock();
           if (dbg & 2) { v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
           else {
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
@@ -552,18 +592,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
               gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
             }
           }
+          if (pprof) { t1 = tc_clock(); acc_comp += t1 - t0; }
           if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+          if (pprof) { t2 = tc_clock(); acc_wait += t2 - t1; }
           if (!(dbg & (2 | 256))) {
             char* st = cv.stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) store_piece<F16>(st, trow[i], hf, pc, v[i]);
           }
+          if (pprof) { t3 = tc_clock(); acc_store += t3 - t2; }
           if (!F16 || (hf & 1)) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->full_x[s]);
             ++gc;
           }
+          if (pprof) acc_fence += tc_clock() - t3;
+        }
+        if (pprof) {
+          atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU (+ issue of next gathers)
+          atomicAdd(&g_tc_prof[10], (unsigned long long)acc_wait);   // waiting for the stage to be released by the MMAs
+          atomicAdd(&g_tc_prof[11], (unsigned long long)acc_store);  // split + swizzled stores
+          atomicAdd(&g_tc_prof[12], (unsigned long long)acc_fence);  // fence.proxy.async + arrive
+          atomicAdd(&g_tc_prof[13], 1ull);
+          acc_comp = acc_wait = acc_store = acc_fence = 0;
         }
       }
     }
@@ -586,7 +638,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
 // =====================================================================================================
 // launchers
 // =====================================================================================================
-static size_t gemm_smem_bytes() { return kTcSmemBase; }
+static size_t gemm_smem_bytes() { return kTcSmemBase + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE; }
 static size_t edge_smem_bytes() { return kTcSmemBase + sizeof(EdgeExtra); }
 
 int configure_tc_kernels() {

@@ -258,6 +258,9 @@ __device__ __forceinline__ void control_init(Control* c) {
 // ---- MMA issuer (one thread): per tile, per chunk: 4 k-steps x 3 split products ------------------------------------------
 // bring-up / diagnosis switch (see dsb_tc.cu); this header is included by exactly one translation unit
 __device__ int g_tc_debug = 0;
+// cycle accounting of one epilogue warp and one producer warp per CTA (enabled by g_tc_debug & 512; profiles/tc_ablate.py)
+__device__ unsigned long long g_tc_prof[32];
+__device__ __forceinline__ long long tc_clock() { return clock64(); }
 template <bool F16>
 __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile) {
   const uint32_t tmem = ctl->tmem_base;

@@ -20,16 +20,34 @@ net.defer_status_check = True
 inp = [x.cuda() for x in syn.synthetic_denoiser_inputs(cfg, [25] * B, [175] * B, seed=3)]
 lib = _native.load()
 lib.dsb_debug_set_tc_flags.argtypes = [C.c_int]
+lib.dsb_debug_read_tc_prof.argtypes = [C.POINTER(C.c_uint64)]
+
+
+def read_prof():
+    buf = (C.c_uint64 * 32)()
+    lib.dsb_debug_read_tc_prof(buf)
+    return list(buf)
 with torch.no_grad():
     net(*inp)
     net.set_profiling(True)
     for flags in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 8, 3, 5, 6, 7, 15]:
         lib.dsb_debug_set_tc_flags(flags)
+        read_prof()
         net(*inp); net(*inp)
         net.collect_profile(reset=True)
         for _ in range(5):
             net(*inp)
         p = net.collect_profile(reset=True)
+        if flags & 512:
+            c = read_prof()
+            nt, npv = max(c[3], 1), max(c[13], 1)
+            print(f'   epilogue warp0 per virtual tile (cycles): wait {c[0] / nt:8.0f}  pass1 {c[1] / nt:8.0f}  pass2 {c[2] / nt:8.0f}   [TMEM ld: pass1 {c[4] / nt:7.0f} pass2 {c[5] / nt:7.0f}; pass2 scale+STS+syncwarp {c[6] / nt:7.0f}]  (n={nt})')
+            print(f'   producer thread0 per virtual tile (cycles): tile-start {c[8] / npv:7.0f}  compute+gather {c[9] / npv:8.0f}  wait-empty {c[10] / npv:8.0f}  '
+                  f'store {c[11] / npv:7.0f}  fence+arrive {c[12] / npv:7.0f}   (n={npv})')
+        if flags & 512:
+            ng = max(c[23], 1)
+            print(f'   node GEMM CTA0 per launch (cycles): setup {c[16] / ng:7.0f}  epilogue-wait {c[17] / ng:8.0f}  epilogue-work {c[18] / ng:8.0f}  '
+                  f'producers {c[19] / ng:8.0f}  body {c[20] / ng:8.0f}  teardown {c[21] / ng:7.0f}  tiles/launch {c[22] / ng:.2f}  (n={ng})')
         print(f'flags={flags:2d}  edge_gcl {p["edge_gcl"]["ms"] / 30 * 1e3:8.1f} us/launch   edge_coord {p["edge_coord"]["ms"] / 30 * 1e3:8.1f}'
               f'   node_gemm {p["node_gemm"]["ms"] / 120 * 1e3:7.1f} us/launch', flush=True)
     lib.dsb_debug_set_tc_flags(0)
