@@ -209,11 +209,14 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     const std::string q = b + ".gcl_equiv";
     EquivW& Q = w.eq[k];
     const int nm = c.reflection_equivariant ? 1 : 2;
-    float* W1 = pk.alloc((size_t)H * nm * 2 * H); float* b1 = pk.alloc((size_t)nm * 2 * H);
+    Q.nq = nm * 2 * H;
+    Q.np = (k + 1 < c.n_layers) ? 2 * H : 0;          // merged with the next block's first GCL (same input h)
+    const int ldm = Q.nq + Q.np;
+    float* W1 = pk.alloc((size_t)H * ldm); float* b1 = pk.alloc((size_t)ldm);
     const char* names[2] = {".coord_mlp", ".cross_product_mlp"};
     for (int m = 0; m < 2; ++m) {
       if (m < nm) {
-        first_layer(q + names[m] + ".0", W1, nm * 2 * H, m * H, nm * H + m * H, b1, &Q.wr[m], &Q.wr0[m], &Q.tb[m]);
+        first_layer(q + names[m] + ".0", W1, ldm, m * H, nm * H + m * H, b1, &Q.wr[m], &Q.wr0[m], &Q.tb[m]);
         float* t = pk.alloc((size_t)H * H);
         Q.W2[m] = pk.T(P(q + names[m] + ".2.weight"), H, 0, H, H, t, H, 0);
         Q.b2[m] = cp(q + names[m] + ".2.bias");
@@ -221,19 +224,32 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
         Q.wr[m] = Q.wr0[m] = Q.tb[m] = Q.W2[m] = Q.b2[m] = nullptr;
       }
     }
+    const std::string gnext = "egnn.e_block_" + std::to_string(k + 1) + ".gcl_0.edge_mlp.0";
+    if (Q.np) {
+      const float* Wn = P(gnext + ".weight");
+      pk.T(Wn, ld1, 0, H, H, W1, ldm, Q.nq);           // next GCL: receiver part
+      pk.T(Wn, ld1, H, H, H, W1, ldm, Q.nq + H);       //           sender part
+      if (!dry) pack_copy_kernel<<<(H + 255) / 256, 256>>>(b1 + Q.nq, P(gnext + ".bias"), H);
+    }
     Q.W1 = W1; Q.b1 = b1;
     Q.w3 = cp(q + ".coord_mlp.4.weight");
     Q.iW1 = Q.iW2[0] = Q.iW2[1] = TcImage{nullptr, nullptr, nullptr, nullptr, 1.0f};
     if (H == 256) {
-      Packer::Blk blk[4];
+      Packer::Blk blk[6];
+      int nb = 0;
       for (int m = 0; m < nm; ++m) {
         const float* W = P(q + names[m] + ".0.weight");
-        blk[2 * m] = {W, ld1, 0, H, m * H};                    // receiver block
-        blk[2 * m + 1] = {W, ld1, H, H, nm * H + m * H};       // sender block
+        blk[nb++] = {W, ld1, 0, H, m * H};                    // receiver block
+        blk[nb++] = {W, ld1, H, H, nm * H + m * H};           // sender block
         Packer::Blk b2 = {P(q + names[m] + ".2.weight"), H, 0, H, 0};
         pk.image(&Q.iW2[m], H, H, &b2, 1);
       }
-      pk.image(&Q.iW1, nm * 2 * H, H, blk, 2 * nm);
+      if (Q.np) {
+        const float* Wn = P(gnext + ".weight");
+        blk[nb++] = {Wn, ld1, 0, H, Q.nq};
+        blk[nb++] = {Wn, ld1, H, H, Q.nq + H};
+      }
+      pk.image(&Q.iW1, Q.nq + Q.np, H, blk, nb);
     }
   }
   if (pk.d_absmax) cudaFree(pk.d_absmax);
@@ -259,7 +275,7 @@ static Workspace carve(const dsb_config& c, int64_t NL, int64_t NP, int64_t B, i
   ws.hT = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.hout = (float*)take(sizeof(float) * (size_t)(N + 1) * (((c.joint_nf + (c.condition_time ? 1 : 0)) + 3) & ~3));
   ws.agg = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
-  ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 4 * H);
+  ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 6 * H);
   ws.deg = (int32_t*)take(sizeof(int32_t) * (N + 1));
   ws.row_ptr = (int32_t*)take(sizeof(int32_t) * (N + 2));
   ws.erow = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + 1));
@@ -493,38 +509,39 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   DSB_CUDA_OK(cudaMemsetAsync(ws.agg, 0, hbytes, s));
   DSB_CUDA_OK(cudaMemsetAsync(ws.xagg, 0, sizeof(float4) * (size_t)dm.N, s));
   memsets += 2;
+  // P buffer columns: [0, nq) = coordinate first layer of the current block (receiver block | sender block),
+  // [nq, nq + 2H) = edge first layer (receiver | sender) of the GCL that runs next.
+  const int nq = nm * 2 * H, ldP = nq + 2 * H, nrecv = nm * H;
+  const PView pv_gcl = {ws.P + nq, ldP}, pv_coord = {ws.P, ldP};
+  const bool conditional = dm.n_coord_rows < dm.N;
   for (int l = 0; l < c.n_layers; ++l) {
     for (int sub = 0; sub < c.inv_sublayers; ++sub) {
       const GclW& G = dyn->w.gcl[l][sub];
-      mark(KC_NODE_GEMM);
-      GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P, 2 * H, dm.N, 2 * H, 0, nullptr, 0};
-      DSB_TRY(gemm(g1, G.iW1ab));
+      if (!(sub == 0 && l > 0)) {      // otherwise produced by the previous block's merged GEMM
+        mark(KC_NODE_GEMM);
+        GemmArgs g1 = {ws.h, H, H, nullptr, 0, 0, 1.f, G.W1ab, 2 * H, G.b1ab, nullptr, 0, ws.P + nq, ldP, dm.N, 2 * H, 0, nullptr, 0, 0, 0};
+        DSB_TRY(gemm(g1, G.iW1ab));
+        launches += 1;
+      }
       mark(KC_EDGE_GCL);
-      DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, s));
+      DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
-      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1, nullptr, 0};
+      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1, nullptr, 0, 0, 0};
       DSB_TRY(gemm(g2, G.iW3));
-      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0, ws.agg, H};
+      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0, ws.agg, H, 0, 0};
       DSB_TRY(gemm(g3, G.iW4));
-      launches += 4;
+      launches += 3;
     }
+    // one GEMM for everything that consumes the updated h: this block's coord/cross first layers and the next block's
+    // edge first layer.  In conditional mode the receiver-side coord columns are needed for ligand rows only.
     const EquivW& Q = dyn->w.eq[l];
     mark(KC_NODE_GEMM);
-    const int ldq = nm * 2 * H, nrecv = nm * H;
-    if (dm.n_coord_rows < dm.N) {
-      // conditional mode: the receiver-side first layer is needed only for rows whose coordinates move (ligand rows)
-      GemmArgs g4a = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, ldq, Q.b1, nullptr, 0, ws.P, ldq, dm.n_coord_rows, nrecv, 0, nullptr, 0};
-      DSB_TRY(gemm(g4a, Q.iW1, 0));
-      GemmArgs g4b = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1 + nrecv, ldq, Q.b1 + nrecv, nullptr, 0, ws.P + nrecv, ldq, dm.N, nrecv, 0, nullptr, 0};
-      DSB_TRY(gemm(g4b, Q.iW1, nrecv / 256));
-      launches += 1;
-    } else {
-      GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, ldq, Q.b1, nullptr, 0, ws.P, ldq, dm.N, ldq, 0, nullptr, 0};
-      DSB_TRY(gemm(g4, Q.iW1));
-    }
+    GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, Q.nq + Q.np, Q.b1, nullptr, 0, ws.P, ldP, dm.N, Q.nq + Q.np, 0, nullptr, 0,
+                   conditional ? dm.n_coord_rows : 0, conditional ? nrecv : 0};
+    DSB_TRY(gemm(g4, Q.iW1));
     mark(KC_EDGE_COORD);
-    DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, f16, status, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, s));
+    DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, pv_coord, f16, status, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, pv_coord, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];
     mark(KC_COORD_FINISH);
     DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
@@ -535,7 +552,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   mark(KC_NODE_GEMM);
   {
     const int Din = c.joint_nf + (c.condition_time ? 1 : 0), Dpad = (Din + 3) & ~3;
-    GemmArgs go = {ws.h, H, H, nullptr, 0, 0, 1.f, dyn->w.out_wT, Dpad, dyn->w.out_b, nullptr, 0, ws.hout, Dpad, dm.N, Dpad, 0, nullptr, 0};
+    GemmArgs go = {ws.h, H, H, nullptr, 0, 0, 1.f, dyn->w.out_wT, Dpad, dyn->w.out_b, nullptr, 0, ws.hout, Dpad, dm.N, Dpad, 0, nullptr, 0, 0, 0};
     DSB_TRY(launch_node_gemm(go, s));
     launches += 1;
   }

@@ -401,10 +401,10 @@ int configure_edge_kernels(int H) {
 }
 
 int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w,
-                    const float4* x, cudaStream_t s) {
+                    const float4* x, PView pv, cudaStream_t s) {
   const int H = d->cfg.hidden_nf;
   EdgeGclArgs a;
-  a.P = ws.P; a.ldp = 2 * H; a.x = x; a.row_ptr = ws.row_ptr; a.N = dm.N;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.row_ptr = ws.row_ptr; a.N = dm.N;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.w = w; a.agg = ws.agg;
   const int grid = d->num_sms;
   switch (H) {
@@ -419,12 +419,12 @@ int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, 
 }
 
 int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w,
-                      const float4* x, cudaStream_t s) {
+                      const float4* x, PView pv, cudaStream_t s) {
   const dsb_config& c = d->cfg;
   const int H = c.hidden_nf;
   EdgeCoordArgs a;
   a.nm = c.reflection_equivariant ? 1 : 2;
-  a.P = ws.P; a.ldp = a.nm * 2 * H; a.x = x; a.cent = ws.cent; a.gid = ws.gid;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid;
   a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.w = w;
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh;

@@ -49,8 +49,12 @@ struct EquivW {          // EquivariantUpdate (reference egnn_new.py:69-132); in
   const float* W2[2];    // [H][H]
   const float* b2[2];    // [H]
   const float* w3;       // [H] shared bias-free last layer (egnn_new.py:78)
-  TcImage iW1;                      // Nn = nm*2H, K = H
+  TcImage iW1;                      // Nn = nm*2H (+2H), K = H
   TcImage iW2[2];                   // Nn = H, K = H
+  // The first-layer GEMM of this block's coordinate MLPs is merged with the first-layer GEMM of the NEXT block's first
+  // GCL (both consume the same h): W1/b1/iW1 hold [receiver block | sender block | next W1a | next W1b] (nq + np columns).
+  int nq;                           // nm*2H
+  int np;                           // 2H if a next GCL exists, else 0
 };
 
 struct PackedWeights {
@@ -73,7 +77,7 @@ struct Workspace {
   float4 *cent;                 // [B]
   float4 *xagg;                 // [N] raw segment sums of trans
   float4 *velmean;              // [B]
-  float *h, *hT, *agg, *P;      // [N][H], [N][H], [N][H], [N][4H]
+  float *h, *hT, *agg, *P;      // [N][H], [N][H], [N][H], [N][6H] (Q block of the current layer | P block of the next GCL)
   float *hout;                  // [N][Dpad] embedding_out result
   int32_t *deg, *row_ptr;       // [N], [N+1]
   int32_t *erow, *ecol;         // [Ecap]
@@ -137,6 +141,7 @@ struct GemmArgs {
   float* C; int ldc;
   int M; int Nn; int act;                           // act: 0 none, 1 SiLU
   float* Z; int ldz;                                // optional: Z[m][n] = 0 for every output element (re-arms the aggregate)
+  int dead_rows_from; int dead_cols;                // output block rows >= dead_rows_from x cols < dead_cols is not needed (skipped)
 };
 int launch_node_gemm(const GemmArgs& a, cudaStream_t s);
 int configure_node_kernels();
@@ -153,10 +158,11 @@ int launch_post(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, cons
                 float* out_atoms, float* out_residues, int32_t* status, cudaStream_t s);
 
 // ---- launchers implemented in dsb_edge.cu ----------------------------------------------------------
+struct PView { const float* P; int ldp; };           // where an edge kernel finds its factorised first-layer outputs
 int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w,
-                    const float4* x, cudaStream_t s);
+                    const float4* x, PView pv, cudaStream_t s);
 int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w,
-                      const float4* x, cudaStream_t s);
+                      const float4* x, PView pv, cudaStream_t s);
 int configure_edge_kernels(int H);
 
 // ---- tensor-core path (dsb_tc.cu) --------------------------------------------------------------------
@@ -166,9 +172,9 @@ void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsig
 int configure_tc_kernels();
 int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, int n_tile_off, bool f16, int32_t* status,
                         cudaStream_t s);
-int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, bool f16,
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, PView pv, bool f16,
                        int32_t* status, cudaStream_t s);
-int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, bool f16,
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, PView pv, bool f16,
                          int32_t* status, cudaStream_t s);
 
 // ---- device math helpers ----------------------------------------------------------------------------

@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) node_gemm_kernel(GemmArgs g) {
   __shared__ __align__(16) float Bs[2][GBK][GBN];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  if (g.dead_cols > 0 && m0 >= g.dead_rows_from && n0 + GBN <= g.dead_cols) return;   // whole tile is in the unused block
   const int K = g.K1 + g.K2;
   const int tx = tid & 15, ty = tid >> 4;
 

@@ -144,8 +144,24 @@ struct TcGemmArgs {
   const float* bias; const float* R; int ldr;
   float* C; int ldc; int M; int Nn; int act;
   float* Z; int ldz;
+  int dead_mt; int dead_nt;                    // tiles with m-tile >= dead_mt and n-tile < dead_nt are skipped (dead_nt == 0: none)
   float inv_scale;                             // 3xFP16: 1 / (X_SCALE * weight scale); 1 for 3xTF32
   int32_t* status;
+};
+
+// live-tile enumeration: region A = m-tiles [0, dead_mt) x all n-tiles, region B = m-tiles [dead_mt, ntm) x n-tiles [dead_nt, ntn)
+struct TileMap {
+  int ntn, ntm, dead_mt, dead_nt, nA, n_live;
+  __device__ TileMap(int M, int Nn, int dmt, int dnt) {
+    ntn = Nn / TN; ntm = (M + TM - 1) / TM;
+    dead_nt = dnt; dead_mt = dnt > 0 ? (dmt < ntm ? dmt : ntm) : ntm;
+    nA = dead_mt * ntn;
+    n_live = nA + (ntm - dead_mt) * (ntn - dead_nt);
+  }
+  __device__ void get(int t, int& mt, int& nt) const {
+    if (t < nA) { mt = t / ntn; nt = t - mt * ntn; }
+    else { const int u = t - nA, w = ntn - dead_nt; mt = dead_mt + u / w; nt = dead_nt + (u - (u / w) * w); }
+  }
 };
 
 template <bool F16>
@@ -154,8 +170,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
   const Carve cv = carve_smem(smem_raw);
   Control* ctl = cv.ctl;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntn = g.Nn / TN, ntm = (g.M + TM - 1) / TM;
-  const int n_tiles = ntn * ntm;
+  const TileMap tm(g.M, g.Nn, g.dead_mt, g.dead_nt);
+  const int n_tiles = tm.n_live;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (n_my == 0) return;
   const int K = g.K1 + g.K2, halves = K / TKC, chunks = F16 ? halves / 2 : halves;
@@ -173,8 +189,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     float* T = reinterpret_cast<float*>(cv.extra) + warp * (32 * GEMM_T_STRIDE);
     const int tr = lane >> 3, tc4 = (lane & 7) * 4;
     for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int m0 = (tile / ntn) * TM, n0 = (tile % ntn) * TN;
+      int mt_, nt_;
+      tm.get(blockIdx.x + it * gridDim.x, mt_, nt_);
+      const int m0 = mt_ * TM, n0 = nt_ * TN;
       const int a = it & 1;
       const long long e0 = gprof ? tc_clock() : 0;
       mbar_wait(&ctl->acc_full[a], (it >> 1) & 1);
@@ -241,8 +258,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     };
     const long long p0 = gprof ? tc_clock() : 0;
     for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int m0 = (tile / ntn) * TM;
+      int mt_, nt_;
+      tm.get(blockIdx.x + it * gridDim.x, mt_, nt_);
+      const int m0 = mt_ * TM;
       float4 cur[4], nxt[4];
       load_half(m0, 0, cur);
       for (int hf = 0; hf < halves; ++hf) {
@@ -270,8 +288,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     if (lane == 0) {
       uint32_t gc = 0;
       for (int it = 0; it < n_my; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int nt = tile % ntn;
+        int mt_, nt;
+        tm.get(blockIdx.x + it * gridDim.x, mt_, nt);
         tma_role(ctl, cv.stages, g.Bhi + (size_t)nt * chunks * B_CHUNK_FLOATS, g.Blo + (size_t)nt * chunks * B_CHUNK_FLOATS, gc, chunks);
       }
     }
@@ -664,9 +682,12 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   const size_t img_off = (size_t)n_tile_off * (K / (f16 ? TKC16 : TKC)) * B_CHUNK_FLOATS;     // skip the first n-tiles of the image
   a.Bhi = (f16 ? w.h_hi : w.t_hi) + img_off; a.Blo = (f16 ? w.h_lo : w.t_lo) + img_off;
   a.Z = g.Z; a.ldz = g.ldz;
+  a.dead_nt = g.dead_cols / TN; a.dead_mt = a.dead_nt > 0 ? (g.dead_rows_from + TM - 1) / TM : 0;
   a.bias = g.bias; a.R = g.R; a.ldr = g.ldr; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.Nn = g.Nn; a.act = g.act;
   a.inv_scale = f16 ? w.h_inv : 1.0f; a.status = status;
-  const int n_tiles = (g.Nn / TN) * ((g.M + TM - 1) / TM);
+  const int ntn_ = g.Nn / TN, ntm_ = (g.M + TM - 1) / TM;
+  const int dmt_ = a.dead_nt > 0 ? (a.dead_mt < ntm_ ? a.dead_mt : ntm_) : ntm_;
+  const int n_tiles = dmt_ * ntn_ + (ntm_ - dmt_) * (ntn_ - a.dead_nt);
   const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
   if (f16) tc_node_gemm_kernel<true><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
   else tc_node_gemm_kernel<false><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
@@ -674,10 +695,10 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   return 0;
 }
 
-int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, bool f16,
+int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, PView pv, bool f16,
                        int32_t* status, cudaStream_t s) {
   TcEdgeArgs a = {};
-  a.P = ws.P; a.ldp = 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.N;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.N;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.nm = 1;
   a.W2hi[0] = f16 ? w.iW2.h_hi : w.iW2.t_hi; a.W2lo[0] = f16 ? w.iW2.h_lo : w.iW2.t_lo;
   a.inv_scale[0] = f16 ? w.iW2.h_inv : 1.0f; a.inv_scale[1] = 1.0f;
@@ -689,12 +710,12 @@ int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   return 0;
 }
 
-int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, bool f16,
+int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, PView pv, bool f16,
                          int32_t* status, cudaStream_t s) {
   const dsb_config& c = d->cfg;
   TcEdgeArgs a = {};
   a.nm = c.reflection_equivariant ? 1 : 2;
-  a.P = ws.P; a.ldp = a.nm * 2 * H256; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL;
   a.inv_scale[0] = a.inv_scale[1] = 1.0f;
   for (int m = 0; m < a.nm; ++m) {
