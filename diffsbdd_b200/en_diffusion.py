@@ -370,6 +370,104 @@ class EnVariationalDiffusion(nn.Module):
         out_pocket[0] = torch.cat([x_pocket, h_pocket], dim=1)
         return out_lig.squeeze(0), out_pocket.squeeze(0), lig_mask, pocket_mask
 
+    # ---- RePaint-style inpainting with the joint model (en_diffusion.py:653-837) ---------------------------------
+    @staticmethod
+    def get_repaint_schedule(resamplings, jump_length, timesteps):
+        """en_diffusion.py:653-674: number of consecutive denoising steps before each jump back, in execution order."""
+        blocks = []
+        done = 0
+        while done < timesteps:
+            step = jump_length if done + jump_length < timesteps else timesteps - done
+            if blocks:
+                blocks[-1] += step
+                if step == jump_length and done + jump_length < timesteps:
+                    blocks.extend([jump_length] * (resamplings - 1))
+            else:
+                blocks.extend([jump_length] * resamplings if done + jump_length < timesteps else [step])
+            done += step
+        return blocks[::-1]
+
+    def _fixed_com(self, x_lig, x_pocket, lig_sel, pocket_sel, lig_mask, pocket_mask):
+        """COM of the fixed ligand+pocket nodes per graph."""
+        return scatter_mean(torch.cat((x_lig[lig_sel], x_pocket[pocket_sel])),
+                            torch.cat((lig_mask[lig_sel], pocket_mask[pocket_sel])), dim=0)
+
+    @torch.no_grad()
+    def inpaint(self, ligand, pocket, lig_fixed, pocket_fixed, resamplings=1, jump_length=1, return_frames=1,
+                timesteps=None):
+        """en_diffusion.py:677-837: sample the free nodes while the fixed ones follow q(z_s | x)."""
+        timesteps = self.T if timesteps is None else timesteps
+        assert 0 < return_frames <= timesteps
+        assert timesteps % return_frames == 0
+        assert jump_length == 1 or return_frames == 1, "Chain visualization is only implemented for jump_length=1"
+        if len(lig_fixed.size()) == 1:
+            lig_fixed = lig_fixed.unsqueeze(1)
+        if len(pocket_fixed.size()) == 1:
+            pocket_fixed = pocket_fixed.unsqueeze(1)
+        ligand, pocket = self.normalize(ligand, pocket)
+        lmask, pmask = ligand['mask'], pocket['mask']
+        lsel, psel = lig_fixed.bool().view(-1), pocket_fixed.bool().view(-1)
+        n_samples = len(ligand['size'])
+        nd = self.n_dims
+        combined_mask = torch.cat((lmask, pmask))
+        xh0_lig = torch.cat([ligand['x'], ligand['one_hot']], dim=1)
+        xh0_pocket = torch.cat([pocket['x'], pocket['one_hot']], dim=1)
+
+        # centre the system on the COM of the known nodes (en_diffusion.py:707-717)
+        mean_known = self._fixed_com(ligand['x'], pocket['x'], lsel, psel, lmask, pmask)
+        xh0_lig[:, :nd] = xh0_lig[:, :nd] - mean_known[lmask]
+        xh0_pocket[:, :nd] = xh0_pocket[:, :nd] - mean_known[pmask]
+
+        z_lig, z_pocket = self.sample_combined_position_feature_noise(lmask, pmask)
+        out_lig = torch.zeros((return_frames,) + z_lig.size(), device=z_lig.device)
+        out_pocket = torch.zeros((return_frames,) + z_pocket.size(), device=z_pocket.device)
+
+        schedule = self.get_repaint_schedule(resamplings, jump_length, timesteps)
+        s = timesteps - 1
+        for i, n_denoise in enumerate(schedule):
+            for j in range(n_denoise):
+                s_array = torch.full((n_samples, 1), fill_value=s, device=z_lig.device)
+                t_array = (s_array + 1) / timesteps
+                s_array = s_array / timesteps
+                gamma_s = self.inflate_batch_array(self.gamma(s_array), ligand['x'])
+                # known nodes: forward-noised data; unknown nodes: one reverse step (en_diffusion.py:741-749)
+                zk_lig, zk_pocket, _, _ = self.noised_representation(xh0_lig, xh0_pocket, lmask, pmask, gamma_s)
+                zu_lig, zu_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, z_pocket, lmask, pmask)
+                # align the COM of the noised known part with the denoised one (en_diffusion.py:751-772)
+                shift = self._fixed_com(zu_lig[:, :nd], zu_pocket[:, :nd], lsel, psel, lmask, pmask) - \
+                    self._fixed_com(zk_lig[:, :nd], zk_pocket[:, :nd], lsel, psel, lmask, pmask)
+                zk_lig[:, :nd] = zk_lig[:, :nd] + shift[lmask]
+                zk_pocket[:, :nd] = zk_pocket[:, :nd] + shift[pmask]
+                z_lig = zk_lig * lig_fixed + zu_lig * (1 - lig_fixed)
+                z_pocket = zk_pocket * pocket_fixed + zu_pocket * (1 - pocket_fixed)
+                self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :nd], z_pocket[:, :nd]), dim=0), combined_mask)
+
+                if (n_denoise > jump_length or i == len(schedule) - 1) and (s * return_frames) % timesteps == 0:
+                    idx = (s * return_frames) // timesteps
+                    out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, z_pocket)
+
+                if j == n_denoise - 1 and i < len(schedule) - 1:      # jump back jump_length steps (en_diffusion.py:790-807)
+                    t = s + jump_length
+                    t_back = torch.full((n_samples, 1), fill_value=t, device=z_lig.device) / timesteps
+                    gamma_s = self.inflate_batch_array(self.gamma(s_array), ligand['x'])
+                    gamma_t = self.inflate_batch_array(self.gamma(t_back), ligand['x'])
+                    z_lig, z_pocket = self.sample_p_zt_given_zs(z_lig, z_pocket, lmask, pmask, gamma_t, gamma_s)
+                    s = t
+                s -= 1
+
+        x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(z_lig, z_pocket, lmask, pmask, n_samples)
+        self.assert_mean_zero_with_mask(torch.cat((x_lig, x_pocket), dim=0), combined_mask)
+        if return_frames == 1:
+            xc = torch.cat((x_lig, x_pocket))
+            max_cog = scatter_add(xc, combined_mask, dim=0).abs().max().item()
+            if max_cog > 5e-2:
+                print(f'Warning CoG drift with error {max_cog:.3f}. Projecting the positions down.')
+                xc = self.remove_mean_batch(xc, combined_mask)
+                x_lig, x_pocket = xc[:len(x_lig)], xc[len(x_lig):]
+        out_lig[0] = torch.cat([x_lig, h_lig], dim=1)
+        out_pocket[0] = torch.cat([x_pocket, h_pocket], dim=1)
+        return out_lig.squeeze(0), out_pocket.squeeze(0), lmask, pmask
+
     # ---- training-side members: out of scope ----------------------------------------------------------------
     def forward(self, ligand, pocket, return_info=False):
         raise NotImplementedError('training loss is out of scope of diffsbdd_b200 (sampling hot path only)')

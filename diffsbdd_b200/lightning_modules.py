@@ -172,8 +172,15 @@ class LigandPocketDDPM(_Base):
             num_nodes_lig = self.ddpm.size_distribution.sample_conditional(n1=None, n2=pocket['size'])
         num_nodes_lig = torch.clamp(num_nodes_lig + n_nodes_bias, min=n_nodes_min)
         if type(self.ddpm) == EnVariationalDiffusion:
-            raise NotImplementedError('joint-model inpainting (en_diffusion.py:677-837) is not built yet '
-                                      '(SURVEY.md §8 f3)')
+            # joint model: inpaint the ligand with every pocket node fixed (lightning_modules.py:814-835)
+            lig_mask = num_nodes_to_batch_mask(len(num_nodes_lig), num_nodes_lig, self.device)
+            ligand = {'x': torch.zeros((len(lig_mask), self.x_dims), device=self.device, dtype=FLOAT_TYPE),
+                      'one_hot': torch.zeros((len(lig_mask), self.atom_nf), device=self.device, dtype=FLOAT_TYPE),
+                      'size': num_nodes_lig, 'mask': lig_mask}
+            lig_fixed = torch.zeros(len(lig_mask), device=self.device)
+            pocket_fixed = torch.ones(len(pocket['mask']), device=self.device)
+            xh_lig, xh_pocket, lig_mask, pocket_mask = self.ddpm.inpaint(
+                ligand, pocket, lig_fixed, pocket_fixed, timesteps=timesteps, **kwargs)
         elif type(self.ddpm) == ConditionalDDPM:
             xh_lig, xh_pocket, lig_mask, pocket_mask = self.ddpm.sample_given_pocket(
                 pocket, num_nodes_lig, timesteps=timesteps)

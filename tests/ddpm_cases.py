@@ -21,6 +21,27 @@ SAMPLER_CASES = {
 }
 
 
+# joint model (update_pocket_coords=True): EnVariationalDiffusion.sample / .inpaint (en_diffusion.py:839, :677)
+JOINT_CFG = DynamicsConfig(joint_nf=16, hidden_nf=64, n_layers=2, update_pocket_coords=True)
+JOINT_CASES = {
+    'joint_sample_T5': dict(kind='sample', T=5, timesteps=None, frames=1, n_lig=[6, 4], seed=201),
+    'joint_inpaint_T6_r2_j2': dict(kind='inpaint', T=6, timesteps=None, resamplings=2, jump_length=2, frames=1,
+                                   n_lig=[7, 5], n_fixed=2, pocket_fixed=True, seed=202),
+    'joint_inpaint_T8_sub4_frames2': dict(kind='inpaint', T=8, timesteps=4, resamplings=1, jump_length=1, frames=2,
+                                          n_lig=[5, 6], n_fixed=0, pocket_fixed=True, seed=203),
+    'joint_inpaint_T4_r3_partial_pocket': dict(kind='inpaint', T=4, timesteps=None, resamplings=3, jump_length=1,
+                                               frames=1, n_lig=[6, 6], n_fixed=3, pocket_fixed=False, seed=204),
+}
+
+
+def make_pocket_fixed(spec, pocket):
+    """0/1 per pocket node: all fixed, or every third node free (exercises the pocket blend of en_diffusion.py:775)."""
+    f = torch.ones(len(pocket['mask']))
+    if not spec['pocket_fixed']:
+        f[::3] = 0
+    return f
+
+
 def make_pocket(device='cpu'):
     p = syn.synthetic_pocket(DDPM_CFG, N_POCKET, seed=31, spread=3.0)
     return {k: v.to(device) for k, v in p.items()}

@@ -18,7 +18,8 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 from diffsbdd_b200 import synthetic as syn  # noqa: E402
 from oracle import ref_shim  # noqa: E402
-from ddpm_cases import DDPM_CFG, HIST, OracleDynamics, make_pocket, make_ligand, SAMPLER_CASES  # noqa: E402
+from ddpm_cases import (DDPM_CFG, HIST, OracleDynamics, make_pocket, make_ligand, SAMPLER_CASES,  # noqa: E402
+                        JOINT_CFG, JOINT_CASES, make_pocket_fixed)
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ddpm')
 
@@ -44,6 +45,28 @@ def main():
         else:
             lig, _ = make_ligand(spec['n_lig'], 0)
             out = ddpm.diversify(lig, pocket, noising_steps=spec['noising_steps'])
+        np.savez_compressed(os.path.join(OUT, name + '.npz'), xh_lig=out[0].numpy(), xh_pocket=out[1].numpy(),
+                            lig_mask=out[2].numpy(), pocket_mask=out[3].numpy(),
+                            gamma=ddpm.gamma.gamma.detach().numpy())
+        print(name, tuple(out[0].shape), float(out[0].abs().max()))
+    # joint model: the UNMODIFIED reference EnVariationalDiffusion (en_diffusion.py:677, :839)
+    sdj = syn.synthetic_state_dict(JOINT_CFG, 6)
+    for name, spec in JOINT_CASES.items():
+        ddpm = ref.EnVariationalDiffusion(dynamics=OracleDynamics(JOINT_CFG, sdj), atom_nf=JOINT_CFG.atom_nf,
+                                          residue_nf=JOINT_CFG.residue_nf, n_dims=3, timesteps=spec['T'],
+                                          noise_schedule='polynomial_2', noise_precision=5e-4, loss_type='l2',
+                                          norm_values=(1, 4), size_histogram=HIST)
+        ddpm.eval()
+        pocket = make_pocket()
+        torch.manual_seed(spec['seed'])
+        if spec['kind'] == 'sample':
+            out = ddpm.sample(len(spec['n_lig']), torch.tensor(spec['n_lig']), pocket['size'],
+                              return_frames=spec['frames'], timesteps=spec['timesteps'])
+        else:
+            lig, fixed = make_ligand(spec['n_lig'], spec['n_fixed'])
+            out = ddpm.inpaint(lig, pocket, fixed, make_pocket_fixed(spec, pocket), resamplings=spec['resamplings'],
+                               jump_length=spec['jump_length'], return_frames=spec['frames'],
+                               timesteps=spec['timesteps'])
         np.savez_compressed(os.path.join(OUT, name + '.npz'), xh_lig=out[0].numpy(), xh_pocket=out[1].numpy(),
                             lig_mask=out[2].numpy(), pocket_mask=out[3].numpy(),
                             gamma=ddpm.gamma.gamma.detach().numpy())

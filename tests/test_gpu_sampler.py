@@ -165,3 +165,40 @@ def test_graph_loop_statistics():
             xs.append(out[0][:, :3])
         spreads[engine] = float(torch.cat(xs).std())
     assert abs(spreads['eager'] - spreads['graph']) < 0.25 * spreads['eager']
+
+
+def _build_joint(T, device, native):
+    from ddpm_cases import JOINT_CFG
+    from diffsbdd_b200.en_diffusion import EnVariationalDiffusion
+    sd = syn.synthetic_state_dict(JOINT_CFG, 6)
+    if native:
+        dyn = EGNNDynamics.from_config(JOINT_CFG, device=device)
+        dyn.load_state_dict(sd)
+    else:
+        dyn = OracleDynamics(JOINT_CFG, sd)
+    ddpm = EnVariationalDiffusion(dynamics=dyn, atom_nf=JOINT_CFG.atom_nf, residue_nf=JOINT_CFG.residue_nf,
+                                  n_dims=3, timesteps=T, noise_schedule='polynomial_2', noise_precision=5e-4,
+                                  loss_type='l2', norm_values=(1, 4), size_histogram=HIST)
+    return ddpm.to(device).eval()
+
+
+def test_joint_repaint_inpaint_matches_cpu_wrapper_with_injected_noise():
+    """EnVariationalDiffusion.inpaint (en_diffusion.py:677-837) around the native joint denoiser
+    (update_pocket_coords=True): RePaint jumps, pocket partially free."""
+    from ddpm_cases import JOINT_CASES, make_pocket_fixed
+    spec = JOINT_CASES['joint_inpaint_T6_r2_j2']
+    cpu = _build_joint(spec['T'], 'cpu', native=False)
+    cpu.sample_gaussian = _NoiseTape(12)
+    lig, fixed = make_ligand(spec['n_lig'], spec['n_fixed'])
+    pocket = make_pocket()
+    pfix = make_pocket_fixed(dict(pocket_fixed=False), pocket)
+    want = cpu.inpaint(lig, pocket, fixed, pfix, resamplings=2, jump_length=2)
+    gpu = _build_joint(spec['T'], 'cuda', native=True)
+    gpu.sample_gaussian = _NoiseTape(12)
+    lig_g, fixed_g = make_ligand(spec['n_lig'], spec['n_fixed'], device='cuda')
+    got = gpu.inpaint(lig_g, make_pocket('cuda'), fixed_g, pfix.cuda(), resamplings=2, jump_length=2)
+    scale = float(max(want[0][:, :3].abs().max(), want[1][:, :3].abs().max()))
+    assert torch.allclose(got[0][:, :3].cpu(), want[0][:, :3], atol=1e-4 * scale)
+    assert torch.allclose(got[1][:, :3].cpu(), want[1][:, :3], atol=1e-4 * scale)
+    assert torch.equal(got[0][:, 3:].cpu(), want[0][:, 3:])
+    assert torch.equal(got[1][:, 3:].cpu(), want[1][:, 3:])
