@@ -2,6 +2,7 @@
 // orchestration (include/diffsbdd_b200.h).  Host logic only + tiny packing kernels.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -11,6 +12,9 @@
 #include "dsb_internal.cuh"
 
 namespace dsb {
+
+static int pdl_from_env() { const char* e = getenv("DSB_PDL"); return e ? (atoi(e) != 0) : 0; }
+int g_pdl = pdl_from_env();
 
 static thread_local char g_err[512] = "";
 
@@ -92,6 +96,43 @@ __global__ void pack_tb_kernel(float* dst, const float* w1, int lds, int scol, c
   dst[idx] = acc;
 }
 
+// folded affine pairs, accumulated in fp64 and rounded once (see PackedWeights)
+// dst[k*H + c] = sum_j embW[c*Din + j] * enc2W[j*F2 + k]  (k < F2);  dst[F2*H + c] = embW[c*Din + J] when Din > J
+__global__ void pack_pre_kernel(float* dst, float* dst_b, const float* embW, const float* embB, const float* enc2W,
+                                const float* enc2B, int H, int J, int Din, int F2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = F2 + (Din > J ? 1 : 0);
+  if (idx >= (K + 1) * H) return;
+  const int k = idx / H, c = idx - k * H;
+  if (k < F2) {
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) acc += (double)embW[(size_t)c * Din + j] * (double)enc2W[(size_t)j * F2 + k];
+    dst[idx] = (float)acc;
+  } else if (k < K) {
+    dst[idx] = embW[(size_t)c * Din + J];
+  } else {
+    double acc = (double)embB[c];
+    for (int j = 0; j < J; ++j) acc += (double)embW[(size_t)c * Din + j] * (double)enc2B[j];
+    dst_b[c] = (float)acc;
+  }
+}
+// dst[o*H + k] = sum_j dec0W[o*J + j] * outW[j*H + k];  dst_b[o] = dec0B[o] + sum_j dec0W[o*J + j] * outB[j]
+__global__ void pack_dec_kernel(float* dst, float* dst_b, const float* dec0W, const float* dec0B, const float* outW,
+                                const float* outB, int H, int J, int F2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= F2 * (H + 1)) return;
+  const int o = idx / (H + 1), k = idx - o * (H + 1);
+  if (k < H) {
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) acc += (double)dec0W[(size_t)o * J + j] * (double)outW[(size_t)j * H + k];
+    dst[(size_t)o * H + k] = (float)acc;
+  } else {
+    double acc = (double)dec0B[o];
+    for (int j = 0; j < J; ++j) acc += (double)dec0W[(size_t)o * J + j] * (double)outB[j];
+    dst_b[o] = (float)acc;
+  }
+}
+
 struct Packer {
   float* blob; size_t used = 0; bool dry;
   explicit Packer(float* b) : blob(b), dry(b == nullptr) {}
@@ -146,18 +187,22 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
   auto cp = [&](const std::string& n) { return pk.copy(P(n), numel(n)); };
 
   w.aenc0_w = cp("atom_encoder.0.weight"); w.aenc0_b = cp("atom_encoder.0.bias");
-  w.aenc2_w = cp("atom_encoder.2.weight"); w.aenc2_b = cp("atom_encoder.2.bias");
   w.renc0_w = cp("residue_encoder.0.weight"); w.renc0_b = cp("residue_encoder.0.bias");
-  w.renc2_w = cp("residue_encoder.2.weight"); w.renc2_b = cp("residue_encoder.2.bias");
-  w.adec0_w = cp("atom_decoder.0.weight"); w.adec0_b = cp("atom_decoder.0.bias");
   w.adec2_w = cp("atom_decoder.2.weight"); w.adec2_b = cp("atom_decoder.2.bias");
-  w.rdec0_w = cp("residue_decoder.0.weight"); w.rdec0_b = cp("residue_decoder.0.bias");
   w.rdec2_w = cp("residue_decoder.2.weight"); w.rdec2_b = cp("residue_decoder.2.bias");
-  { float* t = pk.alloc((size_t)Din * H); w.emb_wT = pk.T(P("egnn.embedding.weight"), Din, 0, H, Din, t, H, 0); }
-  w.emb_b = cp("egnn.embedding.bias");
-  const int Dpad = (Din + 3) & ~3;
-  { float* t = pk.alloc((size_t)H * Dpad); w.out_wT = pk.T(P("egnn.embedding_out.weight"), H, 0, Din, H, t, Dpad, 0); }
-  { float* t = pk.alloc(Dpad); if (!dry) pack_copy_kernel<<<(Din + 255) / 256, 256>>>(t, P("egnn.embedding_out.bias"), Din); w.out_b = t; }
+  for (int ty = 0; ty < 2; ++ty) {
+    const std::string enc = ty == 0 ? "atom_encoder" : "residue_encoder", dec = ty == 0 ? "atom_decoder" : "residue_decoder";
+    const int F2 = 2 * (ty == 0 ? c.atom_nf : c.residue_nf), K = F2 + (Din > J ? 1 : 0);
+    float* pw = pk.alloc((size_t)K * H); float* pb = pk.alloc(H);
+    float* dw = pk.alloc((size_t)F2 * H); float* db = pk.alloc(F2);
+    if (!dry) {
+      pack_pre_kernel<<<((K + 1) * H + 255) / 256, 256>>>(pw, pb, P("egnn.embedding.weight"), P("egnn.embedding.bias"),
+                                                            P(enc + ".2.weight"), P(enc + ".2.bias"), H, J, Din, F2);
+      pack_dec_kernel<<<(F2 * (H + 1) + 255) / 256, 256>>>(dw, db, P(dec + ".0.weight"), P(dec + ".0.bias"),
+                                                            P("egnn.embedding_out.weight"), P("egnn.embedding_out.bias"), H, J, F2);
+    }
+    w.pre_wT[ty] = pw; w.pre_b[ty] = pb; w.dec_w[ty] = dw; w.dec_b[ty] = db;
+  }
   const float* emb = De > 0 ? P("edge_embedding.weight") : nullptr;
 
   auto first_layer = [&](const std::string& pre, float* W1dst, int ldd, int dcol_recv, int dcol_send, float* b1dst,
@@ -273,11 +318,12 @@ static Workspace carve(const dsb_config& c, int64_t NL, int64_t NP, int64_t B, i
   ws.velmean = (float4*)take(sizeof(float4) * (B + 1));
   ws.h = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.hT = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
-  ws.hout = (float*)take(sizeof(float) * (size_t)(N + 1) * (((c.joint_nf + (c.condition_time ? 1 : 0)) + 3) & ~3));
   ws.agg = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 6 * H);
   ws.deg = (int32_t*)take(sizeof(int32_t) * (N + 1));
   ws.row_ptr = (int32_t*)take(sizeof(int32_t) * (N + 2));
+  ws.vrow_ptr = (int32_t*)take(sizeof(int32_t) * (N + 2));
+  ws.vmap = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + (kRowChunk - 1) * N + 1));
   ws.erow = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + 1));
   ws.ecol = (int32_t*)take(sizeof(int32_t) * (size_t)(Ecap + 1));
   ws.ed0 = (float*)take(sizeof(float) * (size_t)(Ecap + 1));
@@ -548,14 +594,6 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     xcur = xnext;
     launches += 3;
   }
-  // embedding_out as a node GEMM (H -> Din, zero-padded to a multiple of 4 columns), decoders in post_kernel
-  mark(KC_NODE_GEMM);
-  {
-    const int Din = c.joint_nf + (c.condition_time ? 1 : 0), Dpad = (Din + 3) & ~3;
-    GemmArgs go = {ws.h, H, H, nullptr, 0, 0, 1.f, dyn->w.out_wT, Dpad, dyn->w.out_b, nullptr, 0, ws.hout, Dpad, dm.N, Dpad, 0, nullptr, 0, 0, 0};
-    DSB_TRY(launch_node_gemm(go, s));
-    launches += 1;
-  }
   mark(KC_POST);
   DSB_TRY(launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s));
   mark(-1);
@@ -564,6 +602,12 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   dyn->last_launches = launches;
   dyn->last_memsets = memsets;
   return 0;
+}
+
+int dsb_set_programmatic_launch(int enable) {
+  const int old = dsb::g_pdl;
+  if (enable >= 0) dsb::g_pdl = enable != 0;
+  return old;
 }
 
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libdiffsbdd_b200.so (sm_100a only).
 #pragma once
+#include <cstring>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -63,11 +64,17 @@ struct PackedWeights {
   const float *renc0_w, *renc0_b, *renc2_w, *renc2_b;
   const float *adec0_w, *adec0_b, *adec2_w, *adec2_b;
   const float *rdec0_w, *rdec0_b, *rdec2_w, *rdec2_b;
-  const float *emb_wT, *emb_b;      // [Din][H] k-major, [H]
-  const float *out_wT, *out_b;      // [H][Dpad] k-major zero-padded to Dpad = round_up(Din, 4), [Dpad]
+  // folded affine pairs (index 0 = atoms, 1 = residues):
+  //   pre_wT [2F+1][H]  = (embedding.W[:, :J] @ encoder.2.W)^T, last row = embedding.W[:, J] (time column)
+  //   pre_b  [H]        = embedding.b + embedding.W[:, :J] @ encoder.2.b
+  //   dec_w  [2F][H]    = decoder.0.W @ embedding_out.W[:J, :]
+  //   dec_b  [2F]       = decoder.0.b + decoder.0.W @ embedding_out.b[:J]
+  const float *pre_wT[2], *pre_b[2], *dec_w[2], *dec_b[2];
   GclW gcl[kMaxLayers][kMaxSub];
   EquivW eq[kMaxLayers];
 };
+
+constexpr int kRowChunk = 4;     // rows of one receiver start at multiples of this in the padded (virtual) edge order
 
 // ---- workspace carve-up ---------------------------------------------------------------------------
 struct Workspace {
@@ -78,8 +85,8 @@ struct Workspace {
   float4 *xagg;                 // [N] raw segment sums of trans
   float4 *velmean;              // [B]
   float *h, *hT, *agg, *P;      // [N][H], [N][H], [N][H], [N][6H] (Q block of the current layer | P block of the next GCL)
-  float *hout;                  // [N][Dpad] embedding_out result
   int32_t *deg, *row_ptr;       // [N], [N+1]
+  int32_t *vrow_ptr, *vmap;     // [N+1], [Ecap + 3N]: receiver segments padded to multiples of kRowChunk rows (tensor-core edge kernels)
   int32_t *erow, *ecol;         // [Ecap]
   float *ed0;                   // [Ecap]
   size_t bytes;
@@ -130,6 +137,31 @@ void set_error(const char* fmt, ...);
       return DSB_ERR_CUDA;                                                                  \
     }                                                                                       \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// With g_pdl != 0 the forward's kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization:
+// every such kernel triggers its dependents at entry (pdl_trigger) and executes griddepcontrol.wait (pdl_wait)
+// before its first access to global memory a predecessor may have touched, so a kernel's launch latency and
+// prologue (barrier init, TMEM allocation, constant-vector staging) overlap the predecessor's tail.  Both
+// instructions are no-ops for a kernel launched without the attribute.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  if (g_pdl) {
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // ---- launchers implemented in dsb_node.cu ----------------------------------------------------------
 struct GemmArgs {

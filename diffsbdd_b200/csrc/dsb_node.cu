@@ -21,6 +21,8 @@ __device__ __forceinline__ int lower_bound_i64(const int64_t* a, int n, int64_t 
 __global__ void plan_kernel(const int64_t* __restrict__ mask_atoms, const int64_t* __restrict__ mask_res,
                             int NL, int NP, int B, int32_t* __restrict__ lig_off,
                             int32_t* __restrict__ poc_off) {
+  pdl_trigger();
+  pdl_wait();
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g > B) return;
   lig_off[g] = lower_bound_i64(mask_atoms, NL, (int64_t)g);
@@ -30,29 +32,33 @@ __global__ void plan_kernel(const int64_t* __restrict__ mask_atoms, const int64_
 int launch_plan(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const int64_t* mask_atoms,
                 const int64_t* mask_residues, cudaStream_t s) {
   int threads = 128, blocks = (dm.B + 1 + threads - 1) / threads;
-  plan_kernel<<<blocks, threads, 0, s>>>(mask_atoms, mask_residues, dm.NL, dm.NP, dm.B, ws.lig_off, ws.poc_off);
-  DSB_CUDA_OK(cudaGetLastError());
+  DSB_CUDA_OK(launch_k(plan_kernel, blocks, threads, 0, s, mask_atoms, mask_residues, dm.NL, dm.NP, dm.B, ws.lig_off, ws.poc_off));
   return 0;
 }
 
 // =====================================================================================================
 // prep: x/h split, atom/residue encoder (Linear-SiLU-Linear), time channel, embedding Linear(J+1 -> H)
-// (dynamics.py:89-111, egnn_new.py:233).  One CTA = 16 nodes of one type.
+// (dynamics.py:89-111, egnn_new.py:233).  The encoder's second Linear and the embedding are both affine
+// with nothing in between, so they are folded at pack time into one [2F+1][H] matrix per node type
+// (rows: encoder hidden units, last row: the time column of the embedding) -- 2F+1 MACs per output instead
+// of 2F*J + (J+1).  One CTA = 32 nodes of one type; thread = output column.
 // =====================================================================================================
-constexpr int PREP_NODES = 16;
-constexpr int PREP_THREADS = 128;
+constexpr int PREP_NODES = 32;
+constexpr int PREP_THREADS = 256;
 
 struct PrepArgs {
   const float* xh_atoms; const float* xh_res; const float* t; int t_numel;
   const int64_t* mask_atoms; const int64_t* mask_res;
-  int NL, NP, A, R, J, Din, H; int cond_time; int coords_only;
-  const float *aenc0_w, *aenc0_b, *aenc2_w, *aenc2_b, *renc0_w, *renc0_b, *renc2_w, *renc2_b;
-  const float *emb_wT, *emb_b;
+  int NL, NP, A, R, H; int cond_time; int coords_only;
+  const float *aenc0_w, *aenc0_b, *renc0_w, *renc0_b;
+  const float *pre_wT[2], *pre_b[2];
   int32_t* gid; float4* x0; float* h;
 };
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs p) {
-  extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float sm[];
   const int lig_blocks = (p.NL + PREP_NODES - 1) / PREP_NODES;
   const bool is_lig = blockIdx.x < lig_blocks;
   const int F = is_lig ? p.A : p.R;
@@ -65,11 +71,11 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs p) {
   const int ld = 3 + F;
   const int node0 = is_lig ? base : p.NL + base;
   const float *w0 = is_lig ? p.aenc0_w : p.renc0_w, *b0 = is_lig ? p.aenc0_b : p.renc0_b;
-  const float *w2 = is_lig ? p.aenc2_w : p.renc2_w, *b2 = is_lig ? p.aenc2_b : p.renc2_b;
+  const float* wT = p.pre_wT[is_lig ? 0 : 1];
+  const float* bf = p.pre_b[is_lig ? 0 : 1];
 
-  float* s_f = sm;                                 // [16][F]
-  float* s_hid = s_f + PREP_NODES * F;             // [16][2F]
-  float* s_j = s_hid + PREP_NODES * F2;            // [16][Din]
+  float* s_f = sm;                                 // [32][F]
+  float* s_hid = s_f + PREP_NODES * F;             // [2F + 1][32]  k-major; last row = t of the node's graph
   const int tid = threadIdx.x;
 
   for (int i = tid; i < nn; i += PREP_THREADS) {
@@ -78,44 +84,39 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(PrepArgs p) {
     p.gid[node0 + i] = (int)mask[base + i];
   }
   if (p.coords_only) return;
-  for (int i = tid; i < nn * F; i += PREP_THREADS) {
-    int n = i / F, k = i - n * F;
-    s_f[i] = xh[(size_t)(base + n) * ld + 3 + k];
+  for (int i = tid; i < PREP_NODES * F; i += PREP_THREADS) {
+    const int n = i / F, k = i - n * F;
+    s_f[i] = n < nn ? xh[(size_t)(base + n) * ld + 3 + k] : 0.f;
   }
   __syncthreads();
-  for (int i = tid; i < nn * F2; i += PREP_THREADS) {
-    int n = i / F2, o = i - n * F2;
+  for (int i = tid; i < PREP_NODES * F2; i += PREP_THREADS) {
+    const int n = i & (PREP_NODES - 1), o = i >> 5;
     float acc = b0[o];
     for (int k = 0; k < F; ++k) acc = fmaf(s_f[n * F + k], w0[o * F + k], acc);
     s_hid[i] = silu_f(acc);
   }
+  if (p.cond_time && tid < PREP_NODES)              // time channel (dynamics.py:104-111)
+    s_hid[F2 * PREP_NODES + tid] = tid < nn ? ((p.t_numel == 1) ? p.t[0] : p.t[(int)mask[base + tid]]) : 0.f;
   __syncthreads();
-  for (int i = tid; i < nn * p.Din; i += PREP_THREADS) {
-    int n = i / p.Din, o = i - n * p.Din;
-    float v;
-    if (o < p.J) {
-      float acc = b2[o];
-      for (int k = 0; k < F2; ++k) acc = fmaf(s_hid[n * F2 + k], w2[o * F2 + k], acc);
-      v = acc;
-    } else {  // time channel (dynamics.py:104-111)
-      v = (p.t_numel == 1) ? p.t[0] : p.t[(int)mask[base + n]];
-    }
-    s_j[i] = v;
-  }
-  __syncthreads();
+  const int K = F2 + (p.cond_time ? 1 : 0);
   for (int c = tid; c < p.H; c += PREP_THREADS) {
-    float acc[PREP_NODES];
-    const float bias = p.emb_b[c];
+    const float bias = bf[c];
+#pragma unroll 1
+    for (int n0 = 0; n0 < nn; n0 += 8) {
+      float acc[8];
 #pragma unroll
-    for (int n = 0; n < PREP_NODES; ++n) acc[n] = bias;
-    for (int k = 0; k < p.Din; ++k) {
-      const float w = p.emb_wT[(size_t)k * p.H + c];
+      for (int j = 0; j < 8; ++j) acc[j] = bias;
+      for (int k = 0; k < K; ++k) {
+        const float w = __ldg(wT + (size_t)k * p.H + c);
+        const float4 ha = *reinterpret_cast<const float4*>(s_hid + k * PREP_NODES + n0);
+        const float4 hb = *reinterpret_cast<const float4*>(s_hid + k * PREP_NODES + n0 + 4);
+        acc[0] = fmaf(ha.x, w, acc[0]); acc[1] = fmaf(ha.y, w, acc[1]); acc[2] = fmaf(ha.z, w, acc[2]); acc[3] = fmaf(ha.w, w, acc[3]);
+        acc[4] = fmaf(hb.x, w, acc[4]); acc[5] = fmaf(hb.y, w, acc[5]); acc[6] = fmaf(hb.z, w, acc[6]); acc[7] = fmaf(hb.w, w, acc[7]);
+      }
 #pragma unroll
-      for (int n = 0; n < PREP_NODES; ++n) acc[n] = fmaf(s_j[n * p.Din + k], w, acc[n]);
+      for (int j = 0; j < 8; ++j)
+        if (n0 + j < nn) p.h[(size_t)(node0 + n0 + j) * p.H + c] = acc[j];
     }
-#pragma unroll
-    for (int n = 0; n < PREP_NODES; ++n)
-      if (n < nn) p.h[(size_t)(node0 + n) * p.H + c] = acc[n];
   }
 }
 
@@ -126,20 +127,18 @@ int launch_prep(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, cons
   PrepArgs p;
   p.xh_atoms = xh_atoms; p.xh_res = xh_residues; p.t = t; p.t_numel = (int)t_numel;
   p.mask_atoms = mask_atoms; p.mask_res = mask_residues;
-  p.NL = dm.NL; p.NP = dm.NP; p.A = c.atom_nf; p.R = c.residue_nf; p.J = c.joint_nf;
-  p.Din = c.joint_nf + (c.condition_time ? 1 : 0); p.H = c.hidden_nf; p.cond_time = c.condition_time;
+  p.NL = dm.NL; p.NP = dm.NP; p.A = c.atom_nf; p.R = c.residue_nf;
+  p.H = c.hidden_nf; p.cond_time = c.condition_time;
   p.coords_only = coords_only ? 1 : 0;
   const PackedWeights& w = d->w;
-  p.aenc0_w = w.aenc0_w; p.aenc0_b = w.aenc0_b; p.aenc2_w = w.aenc2_w; p.aenc2_b = w.aenc2_b;
-  p.renc0_w = w.renc0_w; p.renc0_b = w.renc0_b; p.renc2_w = w.renc2_w; p.renc2_b = w.renc2_b;
-  p.emb_wT = w.emb_wT; p.emb_b = w.emb_b;
+  p.aenc0_w = w.aenc0_w; p.aenc0_b = w.aenc0_b; p.renc0_w = w.renc0_w; p.renc0_b = w.renc0_b;
+  p.pre_wT[0] = w.pre_wT[0]; p.pre_wT[1] = w.pre_wT[1]; p.pre_b[0] = w.pre_b[0]; p.pre_b[1] = w.pre_b[1];
   p.gid = ws.gid; p.x0 = ws.xbuf[0]; p.h = ws.h;
   int Fm = c.atom_nf > c.residue_nf ? c.atom_nf : c.residue_nf;
-  size_t smem = sizeof(float) * PREP_NODES * (size_t)(3 * Fm + p.Din);
+  size_t smem = sizeof(float) * PREP_NODES * (size_t)(3 * Fm + 1);
   int blocks = (dm.NL + PREP_NODES - 1) / PREP_NODES + (dm.NP + PREP_NODES - 1) / PREP_NODES;
   if (blocks == 0) return 0;
-  prep_kernel<<<blocks, PREP_THREADS, smem, s>>>(p);
-  DSB_CUDA_OK(cudaGetLastError());
+  DSB_CUDA_OK(launch_k(prep_kernel, blocks, PREP_THREADS, smem, s, p));
   return 0;
 }
 
@@ -152,10 +151,13 @@ struct EdgeBuildArgs {
   const float4* x; const int32_t* gid; const int32_t* lig_off; const int32_t* poc_off;
   int NL, N; float cut_l, cut_p, cut_i;
   int32_t* deg; const int32_t* row_ptr; int32_t* erow; int32_t* ecol; float* ed0; int64_t Ecap;
+  const int32_t* vrow_ptr; int32_t* vmap;
 };
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) edge_rows_kernel(EdgeBuildArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= a.N) return;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(EdgeBuildArgs a) {
   const float4 xi = a.x[i];
   int count = 0;
   const int base = FILL ? a.row_ptr[i] : 0;
+  const int vbase = FILL ? a.vrow_ptr[i] : 0;
 #pragma unroll 1
   for (int part = 0; part < 2; ++part) {
     const int lo = part == 0 ? a.lig_off[g] : a.NL + a.poc_off[g];
@@ -182,48 +185,61 @@ __global__ void __launch_bounds__(256) edge_rows_kernel(EdgeBuildArgs a) {
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (FILL && keep) {
-        const int64_t e = (int64_t)base + count + __popc(m & ((1u << lane) - 1u));
-        if (e < a.Ecap) { a.erow[e] = i; a.ecol[e] = j; a.ed0[e] = d2; }
+        const int k = count + __popc(m & ((1u << lane) - 1u));
+        const int64_t e = (int64_t)base + k;
+        if (e < a.Ecap) { a.erow[e] = i; a.ecol[e] = j; a.ed0[e] = d2; a.vmap[vbase + k] = (int32_t)e; }
       }
       count += __popc(m);
     }
   }
   if (!FILL && lane == 0) a.deg[i] = count;
+  if (FILL) {       // pad rows of this receiver's segment in the virtual order
+    const int padded = (count + kRowChunk - 1) / kRowChunk * kRowChunk;
+    if (count + lane < padded && (int64_t)base + count <= a.Ecap) a.vmap[vbase + count + lane] = -1;
+  }
 }
 
-// exclusive scan of deg[0..N) -> row_ptr[0..N]; single CTA (N is ~1e4).
+// exclusive scans of deg[0..N) -> row_ptr[0..N] and of the chunk-padded degrees -> vrow_ptr[0..N]; single CTA (N is ~1e4).
 __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ deg, int32_t* __restrict__ row_ptr,
-                                                     int N, int64_t Ecap, int32_t* __restrict__ status) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
+                                                     int32_t* __restrict__ vrow_ptr, int N, int64_t Ecap,
+                                                     int32_t* __restrict__ status) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int s_warp[2][32];
+  __shared__ int s_carry[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  if (tid < 2) s_carry[tid] = 0;
   __syncthreads();
   for (int base = 0; base < N; base += 1024) {
     const int i = base + tid;
     const int v = i < N ? deg[i] : 0;
-    int x = v;
+    const int vp = (v + kRowChunk - 1) / kRowChunk * kRowChunk;
+    int x = v, y = vp;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[wid] = x;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, x, o), b = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) { x += a; y += b; }
+    }
+    if (lane == 31) { s_warp[0][wid] = x; s_warp[1][wid] = y; }
     __syncthreads();
-    if (wid == 0) {
-      int w = s_warp[lane];
+    if (wid < 2) {
+      int w = s_warp[wid][lane];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-      s_warp[lane] = w;
+      for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += a; }
+      s_warp[wid][lane] = w;
     }
     __syncthreads();
-    const int carry = s_carry;
-    const int incl = x + (wid > 0 ? s_warp[wid - 1] : 0) + carry;
-    if (i < N) row_ptr[i] = incl - v;
+    const int incl = x + (wid > 0 ? s_warp[0][wid - 1] : 0) + s_carry[0];
+    const int vincl = y + (wid > 0 ? s_warp[1][wid - 1] : 0) + s_carry[1];
+    if (i < N) { row_ptr[i] = incl - v; vrow_ptr[i] = vincl - vp; }
     __syncthreads();
-    if (tid == 1023) s_carry = incl;
+    if (tid == 1023) { s_carry[0] = incl; s_carry[1] = vincl; }
     __syncthreads();
   }
   if (tid == 0) {
-    const int E = s_carry;
+    const int E = s_carry[0];
     row_ptr[N] = E;
+    vrow_ptr[N] = s_carry[1];
     if (status) {
       status[1] = E;
       if ((int64_t)E > Ecap) atomicOr(&status[2], 1);
@@ -238,11 +254,12 @@ int launch_edges(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, int
   a.NL = dm.NL; a.N = dm.N; a.cut_l = c.edge_cutoff_ligand; a.cut_p = c.edge_cutoff_pocket;
   a.cut_i = c.edge_cutoff_interaction;
   a.deg = ws.deg; a.row_ptr = ws.row_ptr; a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.Ecap = dm.Ecap;
+  a.vrow_ptr = ws.vrow_ptr; a.vmap = ws.vmap;
   const int blocks = (dm.N * 32 + 255) / 256;
   if (dm.N == 0) return 0;
-  edge_rows_kernel<false><<<blocks, 256, 0, s>>>(a);
-  scan_kernel<<<1, 1024, 0, s>>>(ws.deg, ws.row_ptr, dm.N, dm.Ecap, status);
-  edge_rows_kernel<true><<<blocks, 256, 0, s>>>(a);
+  DSB_CUDA_OK(launch_k(edge_rows_kernel<false>, blocks, 256, 0, s, a));
+  DSB_CUDA_OK(launch_k(scan_kernel, 1, 1024, 0, s, ws.deg, ws.row_ptr, ws.vrow_ptr, dm.N, dm.Ecap, status));
+  DSB_CUDA_OK(launch_k(edge_rows_kernel<true>, blocks, 256, 0, s, a));
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -256,6 +273,8 @@ __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restr
                                                             float4* __restrict__ xagg, const int32_t* __restrict__ lig_off,
                                                             const int32_t* __restrict__ poc_off, int NL, int n_coord_rows,
                                                             float norm, int apply_update, float4* __restrict__ cent) {
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x;
   const int l0 = lig_off[g], l1 = lig_off[g + 1], p0 = NL + poc_off[g], p1 = NL + poc_off[g + 1];
   const int nl = l1 - l0, n = nl + (p1 - p0);
@@ -297,9 +316,8 @@ __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restr
 int launch_coord_finish(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const float4* x_old,
                         float4* x_new, bool apply_update, cudaStream_t s) {
   if (dm.B == 0) return 0;
-  coord_finish_kernel<<<dm.B, 128, 0, s>>>(x_old, x_new, ws.xagg, ws.lig_off, ws.poc_off, dm.NL, dm.n_coord_rows,
-                                            d->cfg.normalization_factor, apply_update ? 1 : 0, ws.cent);
-  DSB_CUDA_OK(cudaGetLastError());
+  DSB_CUDA_OK(launch_k(coord_finish_kernel, dm.B, 128, 0, s, x_old, x_new, ws.xagg, ws.lig_off, ws.poc_off, dm.NL,
+                       dm.n_coord_rows, d->cfg.normalization_factor, apply_update ? 1 : 0, ws.cent));
   return 0;
 }
 
@@ -310,6 +328,8 @@ int launch_coord_finish(const dsb_dynamics* d, const Dims& dm, const Workspace& 
 __global__ void __launch_bounds__(128) velmean_kernel(const float4* __restrict__ x_fin, const float4* __restrict__ x_in,
                                                        const int32_t* __restrict__ lig_off, const int32_t* __restrict__ poc_off,
                                                        int NL, float4* __restrict__ velmean) {
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x;
   const int l0 = lig_off[g], l1 = lig_off[g + 1], p0 = NL + poc_off[g], p1 = NL + poc_off[g + 1];
   const int nl = l1 - l0, n = nl + (p1 - p0);
@@ -337,15 +357,25 @@ __global__ void __launch_bounds__(128) velmean_kernel(const float4* __restrict__
   }
 }
 
+// embedding_out (H -> J+1, time channel dropped, egnn_new.py:241 / dynamics.py:149) and the decoder's first Linear
+// are folded at pack time into one [2F][H] matrix per node type; a warp owns 4 nodes: lanes split the H axis of
+// the fused first layer (butterfly reduction), the tiny second Linear runs from a per-warp shared buffer.
+constexpr int POST_WARPS = PREP_THREADS / 32;
+constexpr int POST_NPW = PREP_NODES / POST_WARPS;      // nodes per warp (4)
+constexpr int POST_MAX_F2 = 128;
+
 struct PostArgs {
-  const float* hout; int Dpad; const float4* x_fin; const float4* x_in; const int32_t* gid; const float4* velmean;
-  int NL, NP, A, R, J, Din, H; int joint;
-  const float *adec0_w, *adec0_b, *adec2_w, *adec2_b, *rdec0_w, *rdec0_b, *rdec2_w, *rdec2_b;
+  const float* h; const float4* x_fin; const float4* x_in; const int32_t* gid; const float4* velmean;
+  int NL, NP, A, R, H; int joint;
+  const float *dec_w[2], *dec_b[2];
+  const float *adec2_w, *adec2_b, *rdec2_w, *rdec2_b;
   float* out_atoms; float* out_res; int32_t* status;
 };
 
 __global__ void __launch_bounds__(PREP_THREADS) post_kernel(PostArgs p) {
-  extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_hid[POST_WARPS][POST_NPW][POST_MAX_F2];
   const int lig_blocks = (p.NL + PREP_NODES - 1) / PREP_NODES;
   const bool is_lig = blockIdx.x < lig_blocks;
   const int F = is_lig ? p.A : p.R, F2 = 2 * F;
@@ -355,40 +385,66 @@ __global__ void __launch_bounds__(PREP_THREADS) post_kernel(PostArgs p) {
   const int node0 = is_lig ? base : p.NL + base;
   float* out = is_lig ? p.out_atoms : p.out_res;
   const int ld = 3 + F;
-  const float *w0 = is_lig ? p.adec0_w : p.rdec0_w, *b0 = is_lig ? p.adec0_b : p.rdec0_b;
+  const float* w1 = p.dec_w[is_lig ? 0 : 1];
+  const float* b1 = p.dec_b[is_lig ? 0 : 1];
   const float *w2 = is_lig ? p.adec2_w : p.rdec2_w, *b2 = is_lig ? p.adec2_b : p.rdec2_b;
-  float* s_o = sm;                             // [16][J]  embedding_out result, time channel dropped (dynamics.py:149)
-  float* s_hid = s_o + PREP_NODES * p.J;       // [16][2F]
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < nn * p.J; i += PREP_THREADS) {
-    const int n = i / p.J, o = i - n * p.J;
-    s_o[i] = p.hout[(size_t)(node0 + n) * p.Dpad + o];
-  }
-  for (int i = tid; i < nn; i += PREP_THREADS) {
-    const float4 a = p.x_fin[node0 + i], b = p.x_in[node0 + i];
+  if (tid < nn) {
+    const float4 a = p.x_fin[node0 + tid], b = p.x_in[node0 + tid];
     float vx = a.x - b.x, vy = a.y - b.y, vz = a.z - b.z;
     if (isnan(vx) || isnan(vy) || isnan(vz)) atomicOr(&p.status[0], 1);   // dynamics.py:155-159
     if (p.joint) {                                                         // dynamics.py:161-164
-      const float4 m = p.velmean[p.gid[node0 + i]];
+      const float4 m = p.velmean[p.gid[node0 + tid]];
       vx -= m.x; vy -= m.y; vz -= m.z;
     }
-    float* row = out + (size_t)(base + i) * ld;
+    float* row = out + (size_t)(base + tid) * ld;
     row[0] = vx; row[1] = vy; row[2] = vz;
   }
-  __syncthreads();
-  for (int i = tid; i < nn * F2; i += PREP_THREADS) {
-    const int n = i / F2, o = i - n * F2;
-    float acc = b0[o];
-    for (int k = 0; k < p.J; ++k) acc = fmaf(s_o[n * p.J + k], w0[o * p.J + k], acc);
-    s_hid[i] = silu_f(acc);
+
+  const int nl0 = warp * POST_NPW;                  // first local node of this warp
+  if (nl0 >= nn) return;
+  const int H4 = p.H >> 2;
+  float4 hv[POST_NPW][2];
+#pragma unroll
+  for (int j = 0; j < POST_NPW; ++j)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k4 = lane + 32 * q;
+      hv[j][q] = (nl0 + j < nn && k4 < H4)
+                     ? *reinterpret_cast<const float4*>(p.h + (size_t)(node0 + nl0 + j) * p.H + 4 * k4)
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  for (int o = 0; o < F2; ++o) {
+    float acc[POST_NPW];
+#pragma unroll
+    for (int j = 0; j < POST_NPW; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k4 = lane + 32 * q;
+      if (k4 < H4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(w1 + (size_t)o * p.H) + k4);
+#pragma unroll
+        for (int j = 0; j < POST_NPW; ++j)
+          acc[j] = fmaf(w.x, hv[j][q].x, fmaf(w.y, hv[j][q].y, fmaf(w.z, hv[j][q].z, fmaf(w.w, hv[j][q].w, acc[j]))));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int j = 0; j < POST_NPW; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    if (lane < POST_NPW) {
+      const float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      s_hid[warp][lane][o] = silu_f(v + b1[o]);
+    }
   }
-  __syncthreads();
-  for (int i = tid; i < nn * F; i += PREP_THREADS) {
-    const int n = i / F, o = i - n * F;
+  __syncwarp();
+  for (int i = lane; i < POST_NPW * F; i += 32) {
+    const int j = i / F, o = i - j * F;
+    if (nl0 + j >= nn) continue;
     float acc = b2[o];
-    for (int k = 0; k < F2; ++k) acc = fmaf(s_hid[n * F2 + k], w2[o * F2 + k], acc);
-    out[(size_t)(base + n) * ld + 3 + o] = acc;
+    for (int k = 0; k < F2; ++k) acc = fmaf(s_hid[warp][j][k], w2[o * F2 + k], acc);
+    out[(size_t)(base + nl0 + j) * ld + 3 + o] = acc;
   }
 }
 
@@ -396,22 +452,19 @@ int launch_post(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, cons
                 float* out_atoms, float* out_residues, int32_t* status, cudaStream_t s) {
   const dsb_config& c = d->cfg;
   const PackedWeights& w = d->w;
+  static_assert(POST_NPW == 4, "lane select below assumes 4 nodes per warp");
   if (c.update_pocket_coords && dm.B > 0) {
-    velmean_kernel<<<dm.B, 128, 0, s>>>(x_final, ws.xbuf[0], ws.lig_off, ws.poc_off, dm.NL, ws.velmean);
+    DSB_CUDA_OK(launch_k(velmean_kernel, dm.B, 128, 0, s, x_final, ws.xbuf[0], ws.lig_off, ws.poc_off, dm.NL, ws.velmean));
   }
   PostArgs p;
-  p.hout = ws.hout; p.Dpad = ((c.joint_nf + (c.condition_time ? 1 : 0)) + 3) & ~3; p.x_fin = x_final; p.x_in = ws.xbuf[0]; p.gid = ws.gid; p.velmean = ws.velmean;
-  p.NL = dm.NL; p.NP = dm.NP; p.A = c.atom_nf; p.R = c.residue_nf; p.J = c.joint_nf;
-  p.Din = c.joint_nf + (c.condition_time ? 1 : 0); p.H = c.hidden_nf; p.joint = c.update_pocket_coords;
-  p.adec0_w = w.adec0_w; p.adec0_b = w.adec0_b; p.adec2_w = w.adec2_w; p.adec2_b = w.adec2_b;
-  p.rdec0_w = w.rdec0_w; p.rdec0_b = w.rdec0_b; p.rdec2_w = w.rdec2_w; p.rdec2_b = w.rdec2_b;
+  p.h = ws.h; p.x_fin = x_final; p.x_in = ws.xbuf[0]; p.gid = ws.gid; p.velmean = ws.velmean;
+  p.NL = dm.NL; p.NP = dm.NP; p.A = c.atom_nf; p.R = c.residue_nf; p.H = c.hidden_nf; p.joint = c.update_pocket_coords;
+  p.dec_w[0] = w.dec_w[0]; p.dec_w[1] = w.dec_w[1]; p.dec_b[0] = w.dec_b[0]; p.dec_b[1] = w.dec_b[1];
+  p.adec2_w = w.adec2_w; p.adec2_b = w.adec2_b; p.rdec2_w = w.rdec2_w; p.rdec2_b = w.rdec2_b;
   p.out_atoms = out_atoms; p.out_res = out_residues; p.status = status;
-  int Fm = c.atom_nf > c.residue_nf ? c.atom_nf : c.residue_nf;
-  size_t smem = sizeof(float) * PREP_NODES * (size_t)(p.J + 2 * Fm);
   int blocks = (dm.NL + PREP_NODES - 1) / PREP_NODES + (dm.NP + PREP_NODES - 1) / PREP_NODES;
   if (blocks == 0) return 0;
-  post_kernel<<<blocks, PREP_THREADS, smem, s>>>(p);
-  DSB_CUDA_OK(cudaGetLastError());
+  DSB_CUDA_OK(launch_k(post_kernel, blocks, PREP_THREADS, 0, s, p));
   return 0;
 }
 

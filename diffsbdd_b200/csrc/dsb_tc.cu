@@ -88,7 +88,7 @@ extern "C" int dsb_debug_read_tc_prof(unsigned long long* out32) {
 }
 
 // ---- common prologue / epilogue of every TC kernel -----------------------------------------------------------------
-constexpr size_t kControlBytes = 128;      // keeps the per-kernel extras 16-byte aligned for float4 access
+constexpr size_t kControlBytes = 256;      // keeps the per-kernel extras 16-byte aligned for float4 access
 static_assert(sizeof(Control) <= kControlBytes, "Control block grew");
 struct Carve {
   char* stages;
@@ -107,8 +107,8 @@ __device__ __forceinline__ Carve carve_smem(uint8_t* raw) {
 constexpr size_t kTcSmemBase = 1024 + (size_t)NSTAGE * STAGE_BYTES + kControlBytes;
 constexpr int GEMM_T_STRIDE = 36;          // floats; 16-byte aligned rows, conflict-free for row-wise STS.128 and LDS.128
 
-__device__ __forceinline__ void tc_begin(Control* ctl, int warp) {
-  if (threadIdx.x == 0) control_init(ctl);
+__device__ __forceinline__ void tc_begin(Control* ctl, int warp, int scal_full_count = 1) {
+  if (threadIdx.x == 0) control_init(ctl, scal_full_count);
   __syncthreads();
   if (warp == MMA_WARP) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before();
@@ -120,7 +120,6 @@ __device__ __forceinline__ void tc_end(Control* ctl, int warp) {
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(ctl->tmem_base, 512);
 }
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory"); }
 
 __device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float* bhi, const float* blo, uint32_t& g, int chunks) {
   for (int kc = 0; kc < chunks; ++kc, ++g) {
@@ -177,7 +176,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
   const int K = g.K1 + g.K2, halves = K / TKC, chunks = F16 ? halves / 2 : halves;
   const bool gprof = (g_tc_debug & 512) && blockIdx.x == 0;
   const long long k0 = gprof ? tc_clock() : 0;
+  pdl_trigger();
   tc_begin(ctl, warp);
+  pdl_wait();
   const long long k1 = gprof ? tc_clock() : 0;
   if (gprof && threadIdx.x == 0) { atomicAdd(&g_tc_prof[16], (unsigned long long)(k1 - k0)); atomicAdd(&g_tc_prof[23], 1ull); }
 
@@ -201,15 +202,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * TN);
 #pragma unroll 1
       for (int cb = 0; cb < TN / 32; ++cb) {
+        const int n = n0 + cb * 32 + tc4;
+        // residual rows first: their latency hides behind the TMEM load and the transpose
+        float4 rr[8];
+        if (g.R) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = m0 + warp * 32 + 4 * i + tr;
+            rr[i] = row < g.M ? *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
         float v[32];
         tmem_ld32(taddr + cb * 32, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
-        const int n = n0 + cb * 32 + tc4;
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias) bias = *reinterpret_cast<const float4*>(g.bias + n);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + tr;
@@ -219,10 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
             if (F16) { x.x *= g.inv_scale; x.y *= g.inv_scale; x.z *= g.inv_scale; x.w *= g.inv_scale; }
             x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
             if (g.act == 1) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
-            if (g.R) {
-              const float4 rr = *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + n);
-              x.x = rr.x + x.x; x.y = rr.y + x.y; x.z = rr.z + x.z; x.w = rr.w + x.w;
-            }
+            if (g.R) { x.x = rr[i].x + x.x; x.y = rr[i].y + x.y; x.z = rr[i].z + x.z; x.w = rr[i].w + x.w; }
             *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = x;
             if (g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)row * g.ldz + n) = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -257,28 +264,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       }
     };
     const long long p0 = gprof ? tc_clock() : 0;
-    for (int it = 0; it < n_my; ++it) {
-      int mt_, nt_;
-      tm.get(blockIdx.x + it * gridDim.x, mt_, nt_);
-      const int m0 = mt_ * TM;
-      float4 cur[4], nxt[4];
-      load_half(m0, 0, cur);
-      for (int hf = 0; hf < halves; ++hf) {
-        if (hf + 1 < halves) load_half(m0, hf + 1, nxt);
-        const int s = gc & 1;
-        if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-        char* st = cv.stages + (size_t)s * STAGE_BYTES;
+    // one chunk (a full pipeline stage) is prefetched into registers ahead of the one being stored, across tile boundaries
+    constexpr int HPC = F16 ? 2 : 1;
+    auto tile_m0 = [&](int it) { int mt_, nt_; tm.get(blockIdx.x + it * gridDim.x, mt_, nt_); return mt_ * TM; };
+    float4 cur[HPC][4], nxt[HPC][4];
+    int it = 0, kc = 0, m0 = tile_m0(0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, hf, pc, cur[i]);
-        if (!F16 || (hf & 1)) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ctl->full_x[s]);
-          ++gc;
-        }
+    for (int h = 0; h < HPC; ++h) load_half(m0, h, cur[h]);
+    const int total = n_my * chunks;
+    for (int q = 0; q < total; ++q) {
+      int nkc = kc + 1, nit = it, nm0 = m0;
+      if (nkc == chunks) { nkc = 0; nit = it + 1; }
+      if (q + 1 < total) {
+        if (nkc == 0) nm0 = tile_m0(nit);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+        for (int h = 0; h < HPC; ++h) load_half(nm0, nkc * HPC + h, nxt[h]);
       }
+      const int s = gc & 1;
+      mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
+      char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < HPC; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, h, pc, cur[h][i]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+      ++gc;
+#pragma unroll
+      for (int h = 0; h < HPC; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[h][i] = nxt[h][i];
+      it = nit; kc = nkc; m0 = nm0;
     }
     if (gprof && ptid == 0) atomicAdd(&g_tc_prof[19], (unsigned long long)(tc_clock() - p0));    // producers: all tiles of this CTA
   } else if (warp == MMA_WARP) {
@@ -308,24 +325,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 // edge kernels
 // =====================================================================================================
 constexpr int H256 = 256;
-constexpr int EPI_T_STRIDE = 33;
+constexpr int EPI_T_STRIDE = 36;          // 16-byte aligned rows: conflict-free row-wise STS.128 and column-wise LDS.32
+constexpr int NSCAL = 3;                   // scalar buffer sets (tile it uses set it % NSCAL)
+constexpr int SCAL_WARPS = 2;              // warps 14, 15 of the edge kernels: per-edge scalars one tile ahead of the producers
+constexpr int EDGE_THREADS = TC_THREADS + SCAL_WARPS * 32;   // 512
 
 struct EdgeExtra {            // shared memory after Control
   float vec[2][3 * H256];     // per MLP: wr, wr0, b2   (the edge-type table tb stays in global/L1)
   float wa[H256];             // attention weight (GCL) or w3 (coord)
-  float d2[2][TM], d0[2][TM];
-  int row[2][TM], col[2][TM], type[2][TM];
-  float phi[2][TM];           // coord kernel: phi of MLP 0, per tile parity
+  float d2[NSCAL][TM], d0[NSCAL][TM];       // per-edge scalars: NSCAL sets so the scalar warps run a full tile ahead of the
+  int row[NSCAL][TM], col[NSCAL][TM], type[NSCAL][TM];   // producers while the epilogue still reads the set of the tile before
   union {
     float T[EPI_WARPS][32 * EPI_T_STRIDE];                     // GCL: per-warp transpose buffer
-    struct { float dir[2][6][TM]; float T4[EPI_WARPS][32 * 4]; } c;   // coord: directions + small transpose buffer
+    struct { float dir[NSCAL][6][TM]; float T4[EPI_WARPS][32 * 4]; } c;   // coord: directions + small transpose buffer
   } u;
 };
 
 struct TcEdgeArgs {
   const float* P; int ldp;
   const float4* x; const float4* cent; const int32_t* gid;
-  const int32_t* row_ptr; int n_rows;        // edges [0, row_ptr[n_rows])
+  const int32_t* vrow_ptr; const int32_t* vmap; int n_rows;   // virtual rows [0, vrow_ptr[n_rows]): vmap[v] = edge index or -1 (pad)
   const int32_t *erow, *ecol; const float* ed0; int NL;
   int nm;                                    // MLPs per tile: 1 (GCL, reflection-equivariant coord) or 2 (coord + cross)
   const float* W2hi[2]; const float* W2lo[2];   // [8][8192] images
@@ -338,19 +357,14 @@ struct TcEdgeArgs {
   int32_t* status;
 };
 
-// one RED per (receiver segment, column): kept out of line so the unrolled row loop only carries a branch
-__device__ __noinline__ void red_flush(float* dst, int myrow, int src_lane, float sum, int dbg) {
-  const int prow = __shfl_sync(0xffffffffu, myrow, src_lane);
-  if (prow >= 0 && !(dbg & 64)) atomicAdd(dst + (size_t)prow * H256, sum);
-}
-
-// per-edge scalars of tile `e0`, written by the 128 even producer threads
+// per-edge scalars of tile `e0` (thread pr handles edge e0 + pr), written by the scalar warps
 template <bool COORD>
-__device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex, int par, int pr, int e0, int E) {
-  const int e = e0 + pr;
+__device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex, int par, int pr, int v0, int V) {
+  const int vr = v0 + pr;
+  const int e = vr < V ? a.vmap[vr] : -1;
   int r = -1, c = 0, ty = 0; float d2 = 0.f, d0 = 0.f;
   float dir[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (e < E) {
+  if (e >= 0) {
     r = a.erow[e]; c = a.ecol[e]; d0 = a.ed0[e];
     const float4 xi = a.x[r], xj = a.x[c];
     const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
@@ -378,43 +392,48 @@ __device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex,
 
 // Virtual tile vt = tile * nm + m  (m-th MLP of the tile).  par(tile) selects the scalar buffers, a = vt & 1 the accumulator.
 template <bool COORD, bool F16>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
+__global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const Carve cv = carve_smem(smem_raw);
   Control* ctl = cv.ctl;
   EdgeExtra* ex = reinterpret_cast<EdgeExtra*>(cv.extra);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int E = a.row_ptr[a.n_rows];
-  const int n_tiles = (E + TM - 1) / TM;
-  const int n_my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (n_my_tiles == 0) return;
   const int nm = a.nm;
-  const int n_my = n_my_tiles * nm;            // virtual tiles
   constexpr int halves = H256 / TKC;           // 32-k production steps per virtual tile
   constexpr int chunks = F16 ? halves / 2 : halves;
   const bool has_tb = a.tb[0] != nullptr;
 
-  for (int i = threadIdx.x; i < H256; i += TC_THREADS) {
+  pdl_trigger();
+  for (int i = threadIdx.x; i < H256; i += EDGE_THREADS) {
     for (int m = 0; m < nm; ++m) {
       float* v = ex->vec[m];
       v[i] = a.wr[m][i]; v[H256 + i] = a.wr0[m][i]; v[2 * H256 + i] = a.b2[m][i];
     }
     ex->wa[i] = a.wa ? a.wa[i] : 0.f;
   }
-  tc_begin(ctl, warp);        // contains the __syncthreads that publishes the vectors
+  tc_begin(ctl, warp, SCAL_WARPS);        // contains the __syncthreads that publishes the vectors
+  pdl_wait();                 // everything above touches only kernel arguments and constant weights
+  const int E = a.vrow_ptr[a.n_rows];          // virtual rows: every receiver's edges start at a multiple of kRowChunk
+  const int n_tiles = (E + TM - 1) / TM;
+  const int n_my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (n_my_tiles == 0) { tc_end(ctl, warp); return; }
+  const int n_my = n_my_tiles * nm;            // virtual tiles
 
   if (warp < EPI_WARPS) {
     // ------------------------------------------------------------------------------------------ epilogue
     const bool has_att = (!COORD) && a.wa != nullptr;
     const float ba = has_att ? a.ba[0] : 0.f;
     float* T = COORD ? ex->u.c.T4[warp] : ex->u.T[warp];
+    float phi0 = 0.f;
+    const long long ep0 = (!COORD && (g_tc_debug & 512) && warp == 0 && lane == 0) ? tc_clock() : 0;
     for (int vt = 0; vt < n_my; ++vt) {
       const int it = vt / nm, m = vt - it * nm;
-      const int par = it & 1, acc = vt & 1;
-      const bool prof_on = (g_tc_debug & 512) && warp == 0 && lane == 0;
+      const int par = it % NSCAL, acc = vt & 1;
+      const uint32_t sph = (uint32_t)(it / NSCAL) & 1u;          // phase of this use of scalar set `par`
+      const bool prof_on = !COORD && (g_tc_debug & 512) && warp == 0 && lane == 0;     // cycle accounting: GCL kernel only
       long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (prof_on) c0 = tc_clock();
-      if (m == 0) mbar_wait(&ctl->scal_full[par], (it >> 1) & 1);
+      if (m == 0) mbar_wait(&ctl->scal_full[par], sph);
       mbar_wait(&ctl->acc_full[acc], (vt >> 1) & 1);
       tc_fence_after();
       if (prof_on) c1 = tc_clock();
@@ -451,17 +470,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
           }
           s = fmaf(v[4 * q], ww.x, s); s = fmaf(v[4 * q + 1], ww.y, s); s = fmaf(v[4 * q + 2], ww.z, s); s = fmaf(v[4 * q + 3], ww.w, s);
         }
-        if (!COORD) tmem_st32(taddr + cb * 32, v);
+        if (!COORD && !(edbg & 2048)) tmem_st32(taddr + cb * 32, v);
       }
       if (prof_on) { c2 = tc_clock(); atomicAdd(&g_tc_prof[4], (unsigned long long)ld_cyc); }
       if (!COORD) {
         tmem_wait_st();
-        const float gate = has_att ? sigmoid_f(s + ba) : 1.0f;
-        // segment structure of this warp's 32 rows (uniform across the 8 column blocks): segment k covers rows
-        // [seg_lo[k], seg_lo[k+1]) with receiver seg_row[k]; at most 32 segments, typically 1-3.
-        const int prev = __shfl_up_sync(0xffffffffu, myrow, 1);
-        const unsigned seg_start = __ballot_sync(0xffffffffu, lane == 0 || myrow != prev);
-        // pass 2: e = m * gate -> transpose through shared memory -> in-order segmented column sums -> RED
+        if (prof_on) atomicAdd(&g_tc_prof[28], (unsigned long long)(tc_clock() - c2));     // tcgen05.wait::st after pass 1
+        const float gate = myrow >= 0 ? (has_att ? sigmoid_f(s + ba) : 1.0f) : 0.f;    // pad rows share a chunk with real rows: weight 0
+        // Receiver segments start at multiples of kRowChunk rows (virtual edge order), so every chunk of 4 rows belongs to one
+        // receiver (or is padding): no segment search.  crow[k] = receiver of chunk k of this warp's 32 rows.
+        static_assert(kRowChunk == 4, "chunk sums below assume 4-row chunks");
+        int crow[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) crow[k] = ex->row[par][warp * 32 + 4 * k];
+        // pass 2: e = m * gate -> row-wise STS.128 into the per-warp buffer -> each lane reads its column (32 independent
+        // LDS), sums 4-row chunks -> one RED per (chunk, column); REDs to the same receiver meet in L2
 #pragma unroll 1
         for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
@@ -469,33 +492,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
           tmem_ld32(taddr + cb * 32, v);
           const long long l1 = prof_on ? tc_clock() : 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) T[lane * EPI_T_STRIDE + j] = v[j] * gate;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) =
+                make_float4(v[4 * q] * gate, v[4 * q + 1] * gate, v[4 * q + 2] * gate, v[4 * q + 3] * gate);
           __syncwarp();
           if (prof_on) { atomicAdd(&g_tc_prof[5], (unsigned long long)(l1 - l0)); atomicAdd(&g_tc_prof[6], (unsigned long long)(tc_clock() - l1)); }
-          // all 32 rows of this lane's column into registers first (independent LDS), then the in-order segment sums
-          float t[32];
+          const long long g0 = prof_on ? tc_clock() : 0;
+          if (!(edbg & 1024)) {
+            const float* tp = T + lane;
+            float* dst = a.agg + cb * 32 + lane;
+            float t[32];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) t[rr] = T[rr * EPI_T_STRIDE + lane];
-          float* dst = a.agg + cb * 32 + lane;
-          float sum = t[0];
+            for (int rr = 0; rr < 32; ++rr) t[rr] = tp[rr * EPI_T_STRIDE];
 #pragma unroll
-          for (int rr = 1; rr < 32; ++rr) {
-            if ((seg_start >> rr) & 1u) {            // warp-uniform, rare (1-3 segments per 32 rows): real branch
-              red_flush(dst, myrow, rr - 1, sum, edbg);
-              sum = 0.f;
+            for (int k = 0; k < 8; ++k) {
+              const float sum = (t[4 * k] + t[4 * k + 1]) + (t[4 * k + 2] + t[4 * k + 3]);
+              if (crow[k] >= 0 && !(edbg & 64)) atomicAdd(dst + (size_t)crow[k] * H256, sum);
             }
-            sum += t[rr];
           }
-          red_flush(dst, myrow, 31, sum, edbg);
           __syncwarp();
+          if (prof_on) atomicAdd(&g_tc_prof[29], (unsigned long long)(tc_clock() - g0));   // chunk sums + REDs of one column block
         }
       } else {
         // coord: s = phi_m for this edge row
         const int r = warp * 32 + lane;
         if (m == 0 && nm == 2) {
-          ex->phi[par][r] = s;
+          phi0 = s;                 // the same thread owns this edge row for both MLPs of the tile
         } else {
-          const float p0 = (nm == 2) ? ex->phi[par][r] : s;
+          const float p0 = (nm == 2) ? phi0 : s;
           const float p1 = s;
           float tr[3];
 #pragma unroll
@@ -507,21 +531,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
             }
             tr[k] = myrow >= 0 ? t : 0.f;
           }
-          // in-order segmented sum over the warp's 32 rows: lanes 0..2 take one component each
+          // 4-row chunks belong to one receiver: lane = (chunk k, component) sums 4 rows and issues one RED
           T[lane * 4 + 0] = tr[0]; T[lane * 4 + 1] = tr[1]; T[lane * 4 + 2] = tr[2];
           __syncwarp();
-          if (lane < 3) {
-            int cur = -1; float sum = 0.f;
-            float* dst = reinterpret_cast<float*>(a.xagg);
-            for (int rr = 0; rr < 32; ++rr) {
-              const int row = ex->row[par][warp * 32 + rr];
-              if (row != cur) {
-                if (cur >= 0) atomicAdd(dst + (size_t)cur * 4 + lane, sum);
-                cur = row; sum = 0.f;
-              }
-              if (row >= 0) sum += T[rr * 4 + lane];
+          {
+            const int k = lane >> 2, comp = lane & 3;
+            const int crow = ex->row[par][warp * 32 + 4 * k];
+            if (comp < 3 && crow >= 0) {
+              const float sum = (T[(4 * k) * 4 + comp] + T[(4 * k + 1) * 4 + comp]) + (T[(4 * k + 2) * 4 + comp] + T[(4 * k + 3) * 4 + comp]);
+              atomicAdd(reinterpret_cast<float*>(a.xagg) + (size_t)crow * 4 + comp, sum);
             }
-            if (cur >= 0) atomicAdd(dst + (size_t)cur * 4 + lane, sum);
           }
           __syncwarp();
         }
@@ -540,54 +559,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
         if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]);
       }
     }
+    if (!COORD && (g_tc_debug & 512) && warp == 0 && lane == 0) {
+      atomicAdd(&g_tc_prof[14], (unsigned long long)(tc_clock() - ep0));     // epilogue warp 0: whole tile loop of this CTA
+      atomicAdd(&g_tc_prof[15], 1ull);
+    }
   } else if (warp < MMA_WARP) {
     // ------------------------------------------------------------------------------------------ producers
     // Thread mapping (coalesced gathers): producer warp pw owns tile rows [16 pw, 16 pw + 16); lane = (sub-row sr, piece p):
-    // 8 lanes cover one row's contiguous 128 bytes (32 k-values), one LDG.128 instruction covers 4 rows = 4 L1 wavefronts
-    // (the former 2-threads-per-row mapping touched 16 rows per instruction).  A thread handles 4 rows x 4 k per 32-k half.
+    // 8 lanes cover one row's contiguous 128 bytes (32 k-values), one LDG.128 instruction covers 4 rows = 4 L1 wavefronts.
+    // A thread handles 4 rows x 4 k per 32-k half.  The loop is seamless across MLPs and tiles: the gathers of the next
+    // 32-k step (same MLP, next MLP, or the first step of the next tile, whose scalars the scalar warps prepared while this
+    // tile was produced) are issued row by row as soon as the registers of the current step are consumed.
     const int ptid = threadIdx.x - EPI_WARPS * 32;
     const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
     const int dbg = g_tc_debug;
+    const bool pprof = !COORD && (dbg & 512) && ptid == 0;
     uint32_t gc = 0;
-    for (int it = 0; it < n_my_tiles; ++it) {
-      const int par = it & 1;
-      const int e0 = (blockIdx.x + it * gridDim.x) * TM;
-      const bool pprof = (dbg & 512) && ptid == 0;
-      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc_wait = 0, acc_store = 0, acc_comp = 0, acc_fence = 0;
-      if (pprof) t0 = tc_clock();
-      mbar_wait(&ctl->scal_empty[par], ((it >> 1) & 1) ^ 1);   // epilogue finished the tile that last used these buffers
-      if (ptid < TM) edge_scalars<COORD>(a, ex, par, ptid, e0, E);
-      producers_sync();
-      if (ptid == 0) mbar_arrive(&ctl->scal_full[par]);
-      int trow[4]; float pd2[4], pd0[4];
-      const float* Pa[4]; const float* Pb[4]; const float* tbp[4];
+    float pd2[4], pd0[4];
+    const float* Pa[4]; const float* Pb[4]; const float* tbp[4];
+    float4 ga[4], gb[4];
+    auto setup_tile = [&](int it) {
+      const int par = it % NSCAL;
+      mbar_wait(&ctl->scal_full[par], (uint32_t)(it / NSCAL) & 1u);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = 16 * pw + 4 * i + sr;
-        trow[i] = r;
         const int prow = ex->row[par][r] < 0 ? 0 : ex->row[par][r];
         Pa[i] = a.P + (size_t)prow * a.ldp + 4 * pc;                                  // receiver block (+ m*H per MLP)
         Pb[i] = a.P + (size_t)ex->col[par][r] * a.ldp + nm * H256 + 4 * pc;           // sender block
         pd2[i] = ex->d2[par][r]; pd0[i] = ex->d0[par][r];
         tbp[i] = has_tb ? a.tb[0] + ex->type[par][r] * H256 + 4 * pc : nullptr;
       }
+    };
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc_wait = 0, acc_store = 0, acc_comp = 0, acc_fence = 0;
+    const long long pp0 = pprof ? tc_clock() : 0;
+    if (pprof) t0 = tc_clock();
+    setup_tile(0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ga[i] = *reinterpret_cast<const float4*>(Pa[i]);
+      gb[i] = *reinterpret_cast<const float4*>(Pb[i]);
+    }
+    if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(tc_clock() - t0));      // first tile: scalars + first gathers issued
+    for (int it = 0; it < n_my_tiles; ++it) {
       for (int m = 0; m < nm; ++m) {
         const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H256;
         const size_t tb_off = has_tb ? (size_t)(a.tb[m] - a.tb[0]) : 0;
-        float4 ga[4], gb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256);
-          gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256);
-        }
-        if (pprof && m == 0) { t1 = tc_clock(); atomicAdd(&g_tc_prof[8], (unsigned long long)(t1 - t0)); }   // tile start: scalars + first gathers issued
 #pragma unroll 1
         for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
+          const bool same = hf + 1 < halves;
           float4 v[4];
           if (pprof) t0 = tc_clock();
-          if (dbg & 2) { v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
-          else {
+          if (dbg & 2) {
+            v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
 #pragma unroll
@@ -596,27 +622,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
               float u1 = fmaf(pd0[i], r04.y, fmaf(pd2[i], r4.y, ga[i].y + gb[i].y));
               float u2 = fmaf(pd0[i], r04.z, fmaf(pd2[i], r4.z, ga[i].z + gb[i].z));
               float u3 = fmaf(pd0[i], r04.w, fmaf(pd2[i], r4.w, ga[i].w + gb[i].w));
+              if (same) {     // registers of row i are free: issue its gathers of the next step right away
+                ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256 + (hf + 1) * TKC);
+                gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
+              }
               if (has_tb) {
                 const float4 t4 = *reinterpret_cast<const float4*>(tbp[i] + tb_off + hf * TKC);
                 u0 += t4.x; u1 += t4.y; u2 += t4.z; u3 += t4.w;
               }
               v[i] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
             }
-          }
-          if (hf + 1 < halves && !(dbg & (2 | 128))) {
+            if (!same) {
+              if (m + 1 < nm) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256 + (hf + 1) * TKC);
-              gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
+                for (int i = 0; i < 4; ++i) {
+                  ga[i] = *reinterpret_cast<const float4*>(Pa[i] + (m + 1) * H256);
+                  gb[i] = *reinterpret_cast<const float4*>(Pb[i] + (m + 1) * H256);
+                }
+              } else if (it + 1 < n_my_tiles) {
+                setup_tile(it + 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  ga[i] = *reinterpret_cast<const float4*>(Pa[i]);
+                  gb[i] = *reinterpret_cast<const float4*>(Pb[i]);
+                }
+              }
             }
           }
           if (pprof) { t1 = tc_clock(); acc_comp += t1 - t0; }
           if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
           if (pprof) { t2 = tc_clock(); acc_wait += t2 - t1; }
-          if (!(dbg & (2 | 256))) {
+          if (!(dbg & 2)) {
             char* st = cv.stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) store_piece<F16>(st, trow[i], hf, pc, v[i]);
+            for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, hf, pc, v[i]);
           }
           if (pprof) { t3 = tc_clock(); acc_store += t3 - t2; }
           if (!F16 || (hf & 1)) {
@@ -628,7 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
           if (pprof) acc_fence += tc_clock() - t3;
         }
         if (pprof) {
-          atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU (+ issue of next gathers)
+          atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU + issue of next gathers (+ next-tile setup)
           atomicAdd(&g_tc_prof[10], (unsigned long long)acc_wait);   // waiting for the stage to be released by the MMAs
           atomicAdd(&g_tc_prof[11], (unsigned long long)acc_store);  // split + swizzled stores
           atomicAdd(&g_tc_prof[12], (unsigned long long)acc_fence);  // fence.proxy.async + arrive
@@ -637,10 +676,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
         }
       }
     }
+    if (pprof) {
+      atomicAdd(&g_tc_prof[24], (unsigned long long)(tc_clock() - pp0));     // producer thread 0: whole loop of this CTA
+      atomicAdd(&g_tc_prof[25], 1ull);
+    }
   } else if (warp == MMA_WARP) {
     if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
     __syncwarp();
-  } else {
+  } else if (warp == TMA_WARP) {
     if (lane == 0) {
       uint32_t gc = 0;
       for (int vt = 0; vt < n_my; ++vt) {
@@ -649,6 +692,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
       }
     }
     __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ scalar warps
+    // 64 threads, two edges each: erow/ecol -> x[r], x[c] (-> centroid) is a chain of dependent global loads; running it
+    // one tile ahead (double-buffered by tile parity) keeps it off the producers' critical path.
+    const int st = threadIdx.x - (TMA_WARP + 1) * 32;
+    for (int it = 0; it < n_my_tiles; ++it) {
+      const int par = it % NSCAL;
+      const int e0 = (blockIdx.x + it * gridDim.x) * TM;
+      mbar_wait(&ctl->scal_empty[par], ((uint32_t)(it / NSCAL) & 1u) ^ 1u);   // epilogue finished the tile that last used this set
+      edge_scalars<COORD>(a, ex, par, st, e0, E);
+      edge_scalars<COORD>(a, ex, par, st + SCAL_WARPS * 32, e0, E);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->scal_full[par]);
+    }
   }
   tc_end(ctl, warp);
 }
@@ -689,23 +746,20 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   const int dmt_ = a.dead_nt > 0 ? (a.dead_mt < ntm_ ? a.dead_mt : ntm_) : ntm_;
   const int n_tiles = dmt_ * ntn_ + (ntm_ - dmt_) * (ntn_ - a.dead_nt);
   const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
-  if (f16) tc_node_gemm_kernel<true><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
-  else tc_node_gemm_kernel<false><<<grid, TC_THREADS, gemm_smem_bytes(), s>>>(a);
-  DSB_CUDA_OK(cudaGetLastError());
+  DSB_CUDA_OK(launch_k(f16 ? tc_node_gemm_kernel<true> : tc_node_gemm_kernel<false>, grid, TC_THREADS, gemm_smem_bytes(), s, a));
   return 0;
 }
 
 int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, PView pv, bool f16,
                        int32_t* status, cudaStream_t s) {
   TcEdgeArgs a = {};
-  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.N;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.vrow_ptr = ws.vrow_ptr; a.vmap = ws.vmap; a.n_rows = dm.N;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.nm = 1;
   a.W2hi[0] = f16 ? w.iW2.h_hi : w.iW2.t_hi; a.W2lo[0] = f16 ? w.iW2.h_lo : w.iW2.t_lo;
   a.inv_scale[0] = f16 ? w.iW2.h_inv : 1.0f; a.inv_scale[1] = 1.0f;
   a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
   a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg; a.status = status;
-  if (f16) tc_edge_kernel<false, true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
-  else tc_edge_kernel<false, false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<false, true> : tc_edge_kernel<false, false>, d->num_sms, EDGE_THREADS, edge_smem_bytes(), s, a));
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -715,7 +769,7 @@ int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace&
   const dsb_config& c = d->cfg;
   TcEdgeArgs a = {};
   a.nm = c.reflection_equivariant ? 1 : 2;
-  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.row_ptr = ws.row_ptr; a.n_rows = dm.n_coord_rows;
+  a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.cent = ws.cent; a.gid = ws.gid; a.vrow_ptr = ws.vrow_ptr; a.vmap = ws.vmap; a.n_rows = dm.n_coord_rows;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL;
   a.inv_scale[0] = a.inv_scale[1] = 1.0f;
   for (int m = 0; m < a.nm; ++m) {
@@ -725,8 +779,7 @@ int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace&
   }
   a.wa = w.w3; a.ba = nullptr;
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg; a.status = status;
-  if (f16) tc_edge_kernel<true, true><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
-  else tc_edge_kernel<true, false><<<d->num_sms, TC_THREADS, edge_smem_bytes(), s>>>(a);
+  DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<true, true> : tc_edge_kernel<true, false>, d->num_sms, EDGE_THREADS, edge_smem_bytes(), s, a));
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }

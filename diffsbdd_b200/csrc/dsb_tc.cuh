@@ -243,15 +243,16 @@ struct Control {
   uint64_t empty[NSTAGE];      // MMA commit -> producers, TMA (count 1)
   uint64_t acc_full[2];        // MMA commit -> epilogue (count 1)
   uint64_t epi_done[2];        // epilogue -> MMA, producers (count EPI_WARPS)
-  uint64_t scal_full[2];       // producers -> epilogue (count 1): per-edge scalars of the tile are in shared memory
-  uint64_t scal_empty[2];      // epilogue -> producers (count EPI_WARPS): scalar buffers of the tile may be overwritten
+  uint64_t scal_full[3];       // scalar warps -> producers, epilogue (count SCAL_WARPS): per-edge scalars of the tile are in shared memory
+  uint64_t scal_empty[3];      // epilogue -> scalar warps (count EPI_WARPS): scalar buffers of the tile may be overwritten
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-__device__ __forceinline__ void control_init(Control* c) {
+__device__ __forceinline__ void control_init(Control* c, int scal_full_count) {
   for (int s = 0; s < NSTAGE; ++s) { mbar_init(&c->full_x[s], PROD_WARPS); mbar_init(&c->full_w[s], 1); mbar_init(&c->empty[s], 1); }
-  for (int a = 0; a < 2; ++a) { mbar_init(&c->acc_full[a], 1); mbar_init(&c->epi_done[a], EPI_WARPS); mbar_init(&c->scal_full[a], 1); mbar_init(&c->scal_empty[a], EPI_WARPS); }
+  for (int a = 0; a < 2; ++a) { mbar_init(&c->acc_full[a], 1); mbar_init(&c->epi_done[a], EPI_WARPS); }
+  for (int a = 0; a < 3; ++a) { mbar_init(&c->scal_full[a], scal_full_count); mbar_init(&c->scal_empty[a], EPI_WARPS); }
   fence_barrier_init();
 }
 

@@ -121,6 +121,12 @@ int dsb_dynamics_edges(dsb_dynamics* dyn,
 /* Number of kernel launches (memsets excluded) the last dsb_dynamics_forward on this module enqueued. */
 int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
 
+/* Process-wide switch for programmatic dependent launch of the forward's kernels (each kernel's launch and prologue
+ * overlap its predecessor's tail; every kernel executes griddepcontrol.wait before touching data a predecessor may
+ * have written).  enable: 1 on, 0 off, negative = query only.  Returns the previous setting.  Initial value: the
+ * environment variable DSB_PDL (default off).  No effect on results. */
+int dsb_set_programmatic_launch(int enable);
+
 /* ---- arithmetic path.  mode is a bitmask: 1 = node GEMMs, 2 = edge (GCL) kernel, 4 = coordinate edge kernel run on
  * the tensor pipe (tcgen05.mma, accumulators in TMEM) as 3-product split contractions with fp32 accumulation
  * (x.w ~= x_lo.w_hi + x_hi.w_lo + x_hi.w_hi: fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance);

@@ -41,10 +41,12 @@ with torch.no_grad():
         if flags & 512:
             c = read_prof()
             nt, npv = max(c[3], 1), max(c[13], 1)
-            print(f'   epilogue warp0 per virtual tile (cycles): wait {c[0] / nt:8.0f}  pass1 {c[1] / nt:8.0f}  pass2 {c[2] / nt:8.0f}   [TMEM ld: pass1 {c[4] / nt:7.0f} pass2 {c[5] / nt:7.0f}; pass2 scale+STS+syncwarp {c[6] / nt:7.0f}]  (n={nt})')
+            print(f'   epilogue warp0 per virtual tile (cycles): wait {c[0] / nt:8.0f}  pass1 {c[1] / nt:8.0f}  pass2 {c[2] / nt:8.0f}   [TMEM ld: pass1 {c[4] / nt:7.0f} pass2 {c[5] / nt:7.0f}; pass2 scale+STS+syncwarp {c[6] / nt:7.0f}; wait::st {c[28] / nt:7.0f}; segment sums+RED {c[29] / nt:7.0f}]  (n={nt})')
             print(f'   producer thread0 per virtual tile (cycles): tile-start {c[8] / npv:7.0f}  compute+gather {c[9] / npv:8.0f}  wait-empty {c[10] / npv:8.0f}  '
                   f'store {c[11] / npv:7.0f}  fence+arrive {c[12] / npv:7.0f}   (n={npv})')
         if flags & 512:
+            print(f'   whole tile loop per CTA (cycles): epilogue warp0 {c[14] / max(c[15], 1):9.0f}   producer thread0 {c[24] / max(c[25], 1):9.0f}   '
+                  f'(vtiles/CTA {nt / max(c[15], 1):.2f})')
             ng = max(c[23], 1)
             print(f'   node GEMM CTA0 per launch (cycles): setup {c[16] / ng:7.0f}  epilogue-wait {c[17] / ng:8.0f}  epilogue-work {c[18] / ng:8.0f}  '
                   f'producers {c[19] / ng:8.0f}  body {c[20] / ng:8.0f}  teardown {c[21] / ng:7.0f}  tiles/launch {c[22] / ng:.2f}  (n={ng})')
