@@ -13,7 +13,7 @@
 
 namespace dsb {
 
-static int pdl_from_env() { const char* e = getenv("DSB_PDL"); return e ? (atoi(e) != 0) : 0; }
+static int pdl_from_env() { const char* e = getenv("DSB_PDL"); return e ? (atoi(e) != 0) : 1; }
 int g_pdl = pdl_from_env();
 
 static thread_local char g_err[512] = "";

@@ -80,10 +80,10 @@ void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsig
 extern "C" int dsb_debug_set_tc_flags(int flags) {
   return cudaMemcpyToSymbol(tc::g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -3;
 }
-// reads (and clears) the 32 cycle counters accumulated by kernels run with flag 512
+// reads (and clears) the 64 cycle counters accumulated by kernels run with flag 512
 extern "C" int dsb_debug_read_tc_prof(unsigned long long* out32) {
-  if (cudaMemcpyFromSymbol(out32, tc::g_tc_prof, 32 * sizeof(unsigned long long)) != cudaSuccess) return -3;
-  unsigned long long z[32] = {0};
+  if (cudaMemcpyFromSymbol(out32, tc::g_tc_prof, 64 * sizeof(unsigned long long)) != cudaSuccess) return -3;
+  unsigned long long z[64] = {0};
   return cudaMemcpyToSymbol(tc::g_tc_prof, z, sizeof(z)) == cudaSuccess ? 0 : -3;
 }
 
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       const int k = hf * TKC + 4 * pc;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = m0 + 16 * pw + 4 * i + sr;
+        const int m = m0 + 16 * pw + 4 * sr + i;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < g.M) {
           if (k < g.K1) {
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 #pragma unroll
       for (int h = 0; h < HPC; ++h)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, h, pc, cur[h][i]);
+        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, cur[h][i]);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->full_x[s]);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     }
     if (gprof && ptid == 0) atomicAdd(&g_tc_prof[19], (unsigned long long)(tc_clock() - p0));    // producers: all tiles of this CTA
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
+    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks, 0);
     __syncwarp();
   } else {
     if (lane == 0) {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         continue;
       }
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
-      float s = 0.f;
+      f32x2 s01 = pk2(0.f, 0.f), s23 = s01;      // four independent partial dot products
       const int edbg = g_tc_debug;
       long long ld_cyc = 0;
 #pragma unroll 1
@@ -461,17 +461,24 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         for (int q = 0; q < 8; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(b2 + cb * 32 + 4 * q);
           const float4 ww = *reinterpret_cast<const float4*>(ex->wa + cb * 32 + 4 * q);
+          f32x2 a01, a23;
           if (F16) {
-            v[4 * q] = silu_f(fmaf(v[4 * q], inv, bb.x)); v[4 * q + 1] = silu_f(fmaf(v[4 * q + 1], inv, bb.y));
-            v[4 * q + 2] = silu_f(fmaf(v[4 * q + 2], inv, bb.z)); v[4 * q + 3] = silu_f(fmaf(v[4 * q + 3], inv, bb.w));
+            const f32x2 ip = pk2(inv, inv);
+            a01 = fma2(pk2(v[4 * q], v[4 * q + 1]), ip, pk2(bb.x, bb.y));
+            a23 = fma2(pk2(v[4 * q + 2], v[4 * q + 3]), ip, pk2(bb.z, bb.w));
           } else {
-            v[4 * q] = silu_f(v[4 * q] + bb.x); v[4 * q + 1] = silu_f(v[4 * q + 1] + bb.y);
-            v[4 * q + 2] = silu_f(v[4 * q + 2] + bb.z); v[4 * q + 3] = silu_f(v[4 * q + 3] + bb.w);
+            a01 = add2(pk2(v[4 * q], v[4 * q + 1]), pk2(bb.x, bb.y));
+            a23 = add2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(bb.z, bb.w));
           }
-          s = fmaf(v[4 * q], ww.x, s); s = fmaf(v[4 * q + 1], ww.y, s); s = fmaf(v[4 * q + 2], ww.z, s); s = fmaf(v[4 * q + 3], ww.w, s);
+          a01 = silu2(a01); a23 = silu2(a23);
+          upk2(a01, v[4 * q], v[4 * q + 1]); upk2(a23, v[4 * q + 2], v[4 * q + 3]);
+          s01 = fma2(a01, pk2(ww.x, ww.y), s01); s23 = fma2(a23, pk2(ww.z, ww.w), s23);
         }
         if (!COORD && !(edbg & 2048)) tmem_st32(taddr + cb * 32, v);
       }
+      float s0, s1, s2, s3;
+      upk2(s01, s0, s1); upk2(s23, s2, s3);
+      const float s = (s0 + s1) + (s2 + s3);
       if (prof_on) { c2 = tc_clock(); atomicAdd(&g_tc_prof[4], (unsigned long long)ld_cyc); }
       if (!COORD) {
         tmem_wait_st();
@@ -480,9 +487,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         // Receiver segments start at multiples of kRowChunk rows (virtual edge order), so every chunk of 4 rows belongs to one
         // receiver (or is padding): no segment search.  crow[k] = receiver of chunk k of this warp's 32 rows.
         static_assert(kRowChunk == 4, "chunk sums below assume 4-row chunks");
+        // A chunk of padding only (tile tail) has gate 0 on all rows: its sums are exactly 0 and are added to row 0.
         int crow[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) crow[k] = ex->row[par][warp * 32 + 4 * k];
+        for (int k = 0; k < 8; ++k) crow[k] = max(ex->row[par][warp * 32 + 4 * k], 0);
+        const f32x2 gp = pk2(gate, gate);
         // pass 2: e = m * gate -> row-wise STS.128 into the per-warp buffer -> each lane reads its column (32 independent
         // LDS), sums 4-row chunks -> one RED per (chunk, column); REDs to the same receiver meet in L2
 #pragma unroll 1
@@ -493,8 +502,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
           const long long l1 = prof_on ? tc_clock() : 0;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) =
-                make_float4(v[4 * q] * gate, v[4 * q + 1] * gate, v[4 * q + 2] * gate, v[4 * q + 3] * gate);
+          {
+            float4 o;
+            upk2(mul2(pk2(v[4 * q], v[4 * q + 1]), gp), o.x, o.y);
+            upk2(mul2(pk2(v[4 * q + 2], v[4 * q + 3]), gp), o.z, o.w);
+            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) = o;
+          }
           __syncwarp();
           if (prof_on) { atomicAdd(&g_tc_prof[5], (unsigned long long)(l1 - l0)); atomicAdd(&g_tc_prof[6], (unsigned long long)(tc_clock() - l1)); }
           const long long g0 = prof_on ? tc_clock() : 0;
@@ -507,7 +520,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float sum = (t[4 * k] + t[4 * k + 1]) + (t[4 * k + 2] + t[4 * k + 3]);
-              if (crow[k] >= 0 && !(edbg & 64)) atomicAdd(dst + (size_t)crow[k] * H256, sum);
+              atomicAdd(dst + (size_t)crow[k] * H256, sum);
             }
           }
           __syncwarp();
@@ -567,6 +580,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     // ------------------------------------------------------------------------------------------ producers
     // Thread mapping (coalesced gathers): producer warp pw owns tile rows [16 pw, 16 pw + 16); lane = (sub-row sr, piece p):
     // 8 lanes cover one row's contiguous 128 bytes (32 k-values), one LDG.128 instruction covers 4 rows = 4 L1 wavefronts.
+    // Step i handles rows 16 pw + 4 sr + i: the two rows of a half-warp differ in bit 2 of the row index, so their 64-byte
+    // pieces land in different halves of the 128B-swizzled row and the operand STS.64 are bank-conflict free.
     // A thread handles 4 rows x 4 k per 32-k half.  The loop is seamless across MLPs and tiles: the gathers of the next
     // 32-k step (same MLP, next MLP, or the first step of the next tile, whose scalars the scalar warps prepared while this
     // tile was produced) are issued row by row as soon as the registers of the current step are consumed.
@@ -583,7 +598,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       mbar_wait(&ctl->scal_full[par], (uint32_t)(it / NSCAL) & 1u);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = 16 * pw + 4 * i + sr;
+        const int r = 16 * pw + 4 * sr + i;
         const int prow = ex->row[par][r] < 0 ? 0 : ex->row[par][r];
         Pa[i] = a.P + (size_t)prow * a.ldp + 4 * pc;                                  // receiver block (+ m*H per MLP)
         Pb[i] = a.P + (size_t)ex->col[par][r] * a.ldp + nm * H256 + 4 * pc;           // sender block
@@ -618,19 +633,19 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float u0 = fmaf(pd0[i], r04.x, fmaf(pd2[i], r4.x, ga[i].x + gb[i].x));
-              float u1 = fmaf(pd0[i], r04.y, fmaf(pd2[i], r4.y, ga[i].y + gb[i].y));
-              float u2 = fmaf(pd0[i], r04.z, fmaf(pd2[i], r4.z, ga[i].z + gb[i].z));
-              float u3 = fmaf(pd0[i], r04.w, fmaf(pd2[i], r4.w, ga[i].w + gb[i].w));
+              const f32x2 d2p = pk2(pd2[i], pd2[i]), d0p = pk2(pd0[i], pd0[i]);
+              f32x2 u01 = fma2(d0p, pk2(r04.x, r04.y), fma2(d2p, pk2(r4.x, r4.y), add2(pk2(ga[i].x, ga[i].y), pk2(gb[i].x, gb[i].y))));
+              f32x2 u23 = fma2(d0p, pk2(r04.z, r04.w), fma2(d2p, pk2(r4.z, r4.w), add2(pk2(ga[i].z, ga[i].w), pk2(gb[i].z, gb[i].w))));
               if (same) {     // registers of row i are free: issue its gathers of the next step right away
                 ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256 + (hf + 1) * TKC);
                 gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
               }
               if (has_tb) {
                 const float4 t4 = *reinterpret_cast<const float4*>(tbp[i] + tb_off + hf * TKC);
-                u0 += t4.x; u1 += t4.y; u2 += t4.z; u3 += t4.w;
+                u01 = add2(u01, pk2(t4.x, t4.y)); u23 = add2(u23, pk2(t4.z, t4.w));
               }
-              v[i] = make_float4(silu_f(u0), silu_f(u1), silu_f(u2), silu_f(u3));
+              u01 = silu2(u01); u23 = silu2(u23);
+              upk2(u01, v[i].x, v[i].y); upk2(u23, v[i].z, v[i].w);
             }
             if (!same) {
               if (m + 1 < nm) {
@@ -655,7 +670,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
           if (!(dbg & 2)) {
             char* st = cv.stages + (size_t)s * STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * i + sr, hf, pc, v[i]);
+            for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * sr + i, hf, pc, v[i]);
           }
           if (pprof) { t3 = tc_clock(); acc_store += t3 - t2; }
           if (!F16 || (hf & 1)) {
@@ -681,7 +696,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       atomicAdd(&g_tc_prof[25], 1ull);
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks);
+    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks, COORD ? 2 : 1);
     __syncwarp();
   } else if (warp == TMA_WARP) {
     if (lane == 0) {

@@ -260,24 +260,33 @@ __device__ __forceinline__ void control_init(Control* c, int scal_full_count) {
 // bring-up / diagnosis switch (see dsb_tc.cu); this header is included by exactly one translation unit
 __device__ int g_tc_debug = 0;
 // cycle accounting of one epilogue warp and one producer warp per CTA (enabled by g_tc_debug & 512; profiles/tc_ablate.py)
-__device__ unsigned long long g_tc_prof[32];
+__device__ unsigned long long g_tc_prof[64];
 __device__ __forceinline__ long long tc_clock() { return clock64(); }
 template <bool F16>
-__device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile) {
+__device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile, int tag) {
   const uint32_t tmem = ctl->tmem_base;
   const bool skip = (g_tc_debug & 8) != 0;
+  // cycle accounting of the issuing thread (g_tc_debug & 512): slots 32 + 8 tag + {0: wait accumulator, 1: wait W, 2: wait X,
+  // 3: issue, 4: chunks}; tag 0 = node GEMM, 1 = GCL, 2 = coord
+  const bool mprof = (g_tc_debug & 512) != 0;
+  long long w_acc = 0, w_w = 0, w_x = 0, w_iss = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   uint32_t g = 0;
   for (int it = 0; it < n_my_tiles; ++it) {
     const int a = it & 1;
+    if (mprof) q0 = tc_clock();
     mbar_wait(&ctl->epi_done[a], ((it >> 1) & 1) ^ 1);      // accumulator buffer drained by the epilogue
     tc_fence_after();
+    if (mprof) w_acc += tc_clock() - q0;
     const uint32_t d = tmem + (uint32_t)(a * TN);
     for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
       const int s = g & 1;
       const uint32_t par = (g >> 1) & 1;
+      if (mprof) q0 = tc_clock();
       mbar_wait(&ctl->full_w[s], par);
+      if (mprof) q1 = tc_clock();
       mbar_wait(&ctl->full_x[s], par);
       tc_fence_after();
+      if (mprof) { q2 = tc_clock(); w_w += q1 - q0; w_x += q2 - q1; }
       char* st = stages + (size_t)s * STAGE_BYTES;
       const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
       if (!skip)
@@ -295,8 +304,14 @@ __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_ti
         }
       }
       umma_commit(&ctl->empty[s]);          // stage reusable once these MMAs have read it
+      if (mprof) { q3 = tc_clock(); w_iss += q3 - q2; }
     }
     umma_commit(&ctl->acc_full[a]);         // accumulator complete
+  }
+  if (mprof) {
+    unsigned long long* o = g_tc_prof + 32 + 8 * tag;
+    atomicAdd(o + 0, (unsigned long long)w_acc); atomicAdd(o + 1, (unsigned long long)w_w); atomicAdd(o + 2, (unsigned long long)w_x);
+    atomicAdd(o + 3, (unsigned long long)w_iss); atomicAdd(o + 4, (unsigned long long)n_my_tiles * chunks_per_tile);
   }
 }
 

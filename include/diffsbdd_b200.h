@@ -124,7 +124,7 @@ int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
 /* Process-wide switch for programmatic dependent launch of the forward's kernels (each kernel's launch and prologue
  * overlap its predecessor's tail; every kernel executes griddepcontrol.wait before touching data a predecessor may
  * have written).  enable: 1 on, 0 off, negative = query only.  Returns the previous setting.  Initial value: the
- * environment variable DSB_PDL (default off).  No effect on results. */
+ * environment variable DSB_PDL (default on).  No effect on results. */
 int dsb_set_programmatic_launch(int enable);
 
 /* ---- arithmetic path.  mode is a bitmask: 1 = node GEMMs, 2 = edge (GCL) kernel, 4 = coordinate edge kernel run on

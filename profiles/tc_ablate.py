@@ -24,7 +24,7 @@ lib.dsb_debug_read_tc_prof.argtypes = [C.POINTER(C.c_uint64)]
 
 
 def read_prof():
-    buf = (C.c_uint64 * 32)()
+    buf = (C.c_uint64 * 64)()
     lib.dsb_debug_read_tc_prof(buf)
     return list(buf)
 with torch.no_grad():
@@ -47,6 +47,10 @@ with torch.no_grad():
         if flags & 512:
             print(f'   whole tile loop per CTA (cycles): epilogue warp0 {c[14] / max(c[15], 1):9.0f}   producer thread0 {c[24] / max(c[25], 1):9.0f}   '
                   f'(vtiles/CTA {nt / max(c[15], 1):.2f})')
+            for tag, name in enumerate(('node GEMM', 'GCL', 'coord')):
+                o = 32 + 8 * tag
+                nc = max(c[o + 4], 1)
+                print(f'   MMA thread, {name}: per chunk (cycles): wait-accumulator {c[o] / nc:7.0f}  wait-W {c[o + 1] / nc:7.0f}  wait-X {c[o + 2] / nc:7.0f}  issue+commit {c[o + 3] / nc:7.0f}   (chunks={nc})')
             ng = max(c[23], 1)
             print(f'   node GEMM CTA0 per launch (cycles): setup {c[16] / ng:7.0f}  epilogue-wait {c[17] / ng:8.0f}  epilogue-work {c[18] / ng:8.0f}  '
                   f'producers {c[19] / ng:8.0f}  body {c[20] / ng:8.0f}  teardown {c[21] / ng:7.0f}  tiles/launch {c[22] / ng:.2f}  (n={ng})')
