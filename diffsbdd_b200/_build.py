@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_NAME = 'libdiffsbdd_b200.so'
 LIB_PATH = os.path.join(HERE, LIB_NAME)
+INSTR_LIB_PATH = os.path.join(HERE, 'libdiffsbdd_b200_instr.so')   # same sources with -DDSB_TC_INSTRUMENT=1 (profiles/tc_ablate.py)
 SOURCES = ['dsb_api.cu', 'dsb_node.cu', 'dsb_edge.cu', 'dsb_tc.cu']
 HEADERS = [os.path.join(CSRC, 'dsb_internal.cuh'), os.path.join(CSRC, 'dsb_tc.cuh'), os.path.join(HERE, '..', 'include', 'diffsbdd_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -35,23 +36,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA translation unit for sm_100a and link the shared library. Returns its path."""
-    stamp = os.path.join(HERE, 'csrc', '.build_stamp')
+def build(force: bool = False, verbose: bool = False, instrumented: bool = False) -> str:
+    """Compile every CUDA translation unit for sm_100a and link the shared library. Returns its path.
+    instrumented=True builds the ablation / cycle-accounting variant next to the product library."""
+    stamp = os.path.join(HERE, 'csrc', '.build_stamp_instr' if instrumented else '.build_stamp')
+    lib_path = INSTR_LIB_PATH if instrumented else LIB_PATH
+    extra = ['-DDSB_TC_INSTRUMENT=1'] if instrumented else []
     dig = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp):
         with open(stamp) as f:
             if f.read().strip() == dig:
-                return LIB_PATH
+                return lib_path
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, 'csrc', 'build')
+    objdir = os.path.join(HERE, 'csrc', 'build_instr' if instrumented else 'build')
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -59,14 +63,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out, file=sys.stderr)
         if p.returncode != 0:
             raise RuntimeError('nvcc failed: %s\n%s' % (' '.join(cmd), out))
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Wno-deprecated-gpu-targets', '-o', LIB_PATH] + objs
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Wno-deprecated-gpu-targets', '-o', lib_path] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed: %s\n%s' % (' '.join(cmd), r.stdout))
     with open(stamp, 'w') as f:
         f.write(dig)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--instrumented' in sys.argv:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, instrumented=True))

@@ -47,11 +47,12 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    instr = os.environ.get('DSB_INSTRUMENT', '0') not in ('', '0')      # profiling tools only (profiles/tc_ablate.py)
+    path = _build.INSTR_LIB_PATH if instr else _build.LIB_PATH
     if not os.path.exists(path):
         if not build_if_missing:
             raise NativeError(f'{path} is missing: run `python -m diffsbdd_b200._build` (needs nvcc)')
-        _build.build()
+        _build.build(instrumented=instr)
     lib = C.CDLL(path)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
     lib.dsb_last_error.restype = C.c_char_p

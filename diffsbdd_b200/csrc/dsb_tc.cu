@@ -78,6 +78,9 @@ void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsig
 // bring-up / diagnosis only (profiles/tc_ablate.py): 1 skip weight copies, 2 skip producer work, 4 skip epilogue work,
 // 8 skip MMAs.  Results are garbage when non-zero; never set by the product path.
 extern "C" int dsb_debug_set_tc_flags(int flags) {
+#if !DSB_TC_INSTRUMENT
+  if (flags != 0) return -4;      // product build: no instrumentation compiled in
+#endif
   return cudaMemcpyToSymbol(tc::g_tc_debug, &flags, sizeof(int)) == cudaSuccess ? 0 : -3;
 }
 // reads (and clears) the 64 cycle counters accumulated by kernels run with flag 512
@@ -126,7 +129,7 @@ __device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float
     const int s = g & 1;
     mbar_wait(&ctl->empty[s], ((g >> 1) & 1) ^ 1);
     char* st = stages + (size_t)s * STAGE_BYTES + 2 * A_CHUNK_BYTES;
-    if (g_tc_debug & 1) { mbar_arrive(&ctl->full_w[s]); continue; }
+    if (tc_debug() & 1) { mbar_arrive(&ctl->full_w[s]); continue; }
     mbar_arrive_expect_tx(&ctl->full_w[s], 2 * B_CHUNK_BYTES);
     bulk_g2s(st, bhi + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
     bulk_g2s(st + B_CHUNK_BYTES, blo + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (n_my == 0) return;
   const int K = g.K1 + g.K2, halves = K / TKC, chunks = F16 ? halves / 2 : halves;
-  const bool gprof = (g_tc_debug & 512) && blockIdx.x == 0;
+  const bool gprof = (tc_debug() & 512) && blockIdx.x == 0;
   const long long k0 = gprof ? tc_clock() : 0;
   pdl_trigger();
   tc_begin(ctl, warp);
@@ -425,12 +428,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     const float ba = has_att ? a.ba[0] : 0.f;
     float* T = COORD ? ex->u.c.T4[warp] : ex->u.T[warp];
     float phi0 = 0.f;
-    const long long ep0 = (!COORD && (g_tc_debug & 512) && warp == 0 && lane == 0) ? tc_clock() : 0;
+    const long long ep0 = (!COORD && (tc_debug() & 512) && warp == 0 && lane == 0) ? tc_clock() : 0;
     for (int vt = 0; vt < n_my; ++vt) {
       const int it = vt / nm, m = vt - it * nm;
       const int par = it % NSCAL, acc = vt & 1;
       const uint32_t sph = (uint32_t)(it / NSCAL) & 1u;          // phase of this use of scalar set `par`
-      const bool prof_on = !COORD && (g_tc_debug & 512) && warp == 0 && lane == 0;     // cycle accounting: GCL kernel only
+      const bool prof_on = !COORD && (tc_debug() & 512) && warp == 0 && lane == 0;     // cycle accounting: GCL kernel only
       long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (prof_on) c0 = tc_clock();
       if (m == 0) mbar_wait(&ctl->scal_full[par], sph);
@@ -441,14 +444,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       const float* b2 = ex->vec[m] + 2 * H256;
       const float inv = a.inv_scale[m];
       const int myrow = ex->row[par][warp * 32 + lane];
-      if (g_tc_debug & 4) {
+      if (tc_debug() & 4) {
         tc_fence_before(); __syncwarp();
         if (lane == 0) { mbar_arrive(&ctl->epi_done[acc]); if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]); }
         continue;
       }
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
       f32x2 s01 = pk2(0.f, 0.f), s23 = s01;      // four independent partial dot products
-      const int edbg = g_tc_debug;
+      const int edbg = tc_debug();
       long long ld_cyc = 0;
 #pragma unroll 1
       for (int cb = 0; cb < TN / 32; ++cb) {
@@ -572,7 +575,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]);
       }
     }
-    if (!COORD && (g_tc_debug & 512) && warp == 0 && lane == 0) {
+    if (!COORD && (tc_debug() & 512) && warp == 0 && lane == 0) {
       atomicAdd(&g_tc_prof[14], (unsigned long long)(tc_clock() - ep0));     // epilogue warp 0: whole tile loop of this CTA
       atomicAdd(&g_tc_prof[15], 1ull);
     }
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     // tile was produced) are issued row by row as soon as the registers of the current step are consumed.
     const int ptid = threadIdx.x - EPI_WARPS * 32;
     const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
-    const int dbg = g_tc_debug;
+    const int dbg = tc_debug();
     const bool pprof = !COORD && (dbg & 512) && ptid == 0;
     uint32_t gc = 0;
     float pd2[4], pd0[4];
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       for (int m = 0; m < nm; ++m) {
         const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H256;
         const size_t tb_off = has_tb ? (size_t)(a.tb[m] - a.tb[0]) : 0;
-#pragma unroll 1
+#pragma unroll 2
         for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
           const bool same = hf + 1 < halves;

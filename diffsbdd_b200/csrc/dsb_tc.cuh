@@ -259,16 +259,28 @@ __device__ __forceinline__ void control_init(Control* c, int scal_full_count) {
 // ---- MMA issuer (one thread): per tile, per chunk: 4 k-steps x 3 split products ------------------------------------------
 // bring-up / diagnosis switch (see dsb_tc.cu); this header is included by exactly one translation unit
 __device__ int g_tc_debug = 0;
+// Product build: the switch is a compile-time 0, so every ablation branch and cycle counter below folds away.  The
+// instrumented library (libdiffsbdd_b200_instr.so, -DDSB_TC_INSTRUMENT=1, selected with DSB_INSTRUMENT=1) reads it at run time.
+#ifndef DSB_TC_INSTRUMENT
+#define DSB_TC_INSTRUMENT 0
+#endif
+__device__ __forceinline__ int tc_debug() {
+#if DSB_TC_INSTRUMENT
+  return g_tc_debug;
+#else
+  return 0;
+#endif
+}
 // cycle accounting of one epilogue warp and one producer warp per CTA (enabled by g_tc_debug & 512; profiles/tc_ablate.py)
 __device__ unsigned long long g_tc_prof[64];
 __device__ __forceinline__ long long tc_clock() { return clock64(); }
 template <bool F16>
 __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile, int tag) {
   const uint32_t tmem = ctl->tmem_base;
-  const bool skip = (g_tc_debug & 8) != 0;
+  const bool skip = (tc_debug() & 8) != 0;
   // cycle accounting of the issuing thread (g_tc_debug & 512): slots 32 + 8 tag + {0: wait accumulator, 1: wait W, 2: wait X,
   // 3: issue, 4: chunks}; tag 0 = node GEMM, 1 = GCL, 2 = coord
-  const bool mprof = (g_tc_debug & 512) != 0;
+  const bool mprof = (tc_debug() & 512) != 0;
   long long w_acc = 0, w_w = 0, w_x = 0, w_iss = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   uint32_t g = 0;
   for (int it = 0; it < n_my_tiles; ++it) {

@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ.setdefault('DSB_INSTRUMENT', '1')     # the product library compiles the switches out
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
