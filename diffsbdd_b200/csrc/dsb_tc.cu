@@ -203,18 +203,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       const long long e1 = gprof ? tc_clock() : 0;
       if (gprof && threadIdx.x == 0) atomicAdd(&g_tc_prof[17], (unsigned long long)(e1 - (it == 0 ? k1 : e0)));   // epilogue waits for the accumulator
       const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * TN);
-#pragma unroll 1
-      for (int cb = 0; cb < TN / 32; ++cb) {
+      // residual rows of column block cb+1 are requested while block cb is processed (two register sets, loop unrolled by 2)
+      auto load_res = [&](int cb, float4 (&rr)[8]) {
         const int n = n0 + cb * 32 + tc4;
-        // residual rows first: their latency hides behind the TMEM load and the transpose
-        float4 rr[8];
-        if (g.R) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = m0 + warp * 32 + 4 * i + tr;
-            rr[i] = row < g.M ? *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + warp * 32 + 4 * i + tr;
+          rr[i] = row < g.M ? *reinterpret_cast<const float4*>(g.R + (size_t)row * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      auto do_block = [&](int cb, const float4 (&rr)[8]) {
+        const int n = n0 + cb * 32 + tc4;
         float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
         float v[32];
@@ -223,21 +222,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
+        const f32x2 ip = pk2(g.inv_scale, g.inv_scale), b01 = pk2(bias.x, bias.y), b23 = pk2(bias.z, bias.w);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + tr;
           const int row = m0 + warp * 32 + rl;
-          float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+          const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
           if (row < g.M) {
-            if (F16) { x.x *= g.inv_scale; x.y *= g.inv_scale; x.z *= g.inv_scale; x.w *= g.inv_scale; }
-            x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
-            if (g.act == 1) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
-            if (g.R) { x.x = rr[i].x + x.x; x.y = rr[i].y + x.y; x.z = rr[i].z + x.z; x.w = rr[i].w + x.w; }
-            *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = x;
-            if (g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)row * g.ldz + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+            f32x2 x01 = pk2(x.x, x.y), x23 = pk2(x.z, x.w);
+            if (F16) { x01 = fma2(x01, ip, b01); x23 = fma2(x23, ip, b23); }
+            else { x01 = add2(x01, b01); x23 = add2(x23, b23); }
+            if (g.act == 1) { x01 = silu2(x01); x23 = silu2(x23); }
+            if (g.R) { x01 = add2(pk2(rr[i].x, rr[i].y), x01); x23 = add2(pk2(rr[i].z, rr[i].w), x23); }
+            float4 o;
+            upk2(x01, o.x, o.y); upk2(x23, o.z, o.w);
+            if (!(tc_debug() & 32)) {
+              *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
+              if (g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)row * g.ldz + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
         __syncwarp();
+      };
+      float4 ra[8], rb[8];
+      if (g.R) load_res(0, ra);
+#pragma unroll 1
+      for (int cb = 0; cb < ((tc_debug() & 4) ? 0 : TN / 32); cb += 2) {
+        if (g.R) load_res(cb + 1, rb);
+        do_block(cb, ra);
+        if (g.R && cb + 2 < TN / 32) load_res(cb + 2, ra);
+        do_block(cb + 1, rb);
       }
       if (gprof && threadIdx.x == 0) atomicAdd(&g_tc_prof[18], (unsigned long long)(tc_clock() - e1));             // epilogue work of one tile
       tc_fence_before();
@@ -255,50 +269,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + 16 * pw + 4 * sr + i;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < g.M) {
+        if (m < g.M && !(tc_debug() & 2)) {
           if (k < g.K1) {
             x = *reinterpret_cast<const float4*>(g.A1 + (size_t)m * g.lda1 + k);
           } else {
-            x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1));
-            if (g.div2 != 1.0f) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
+            x = *reinterpret_cast<const float4*>(g.A2 + (size_t)m * g.lda2 + (k - g.K1));     // divided by div2 when staged
           }
         }
         v[i] = x;
       }
     };
     const long long p0 = gprof ? tc_clock() : 0;
-    // one chunk (a full pipeline stage) is prefetched into registers ahead of the one being stored, across tile boundaries
+    // Two register sets, each holding one K-chunk (a full pipeline stage) of this thread's rows: the loads of chunk q+2 are
+    // issued right after chunk q has been converted and stored, i.e. they have a whole chunk period more than the L2
+    // latency before they are needed (one-ahead prefetch left the loop bound by that latency: 1.8 k cycles of the MMA
+    // thread's 3.5 k per chunk were spent waiting for the operand).
     constexpr int HPC = F16 ? 2 : 1;
     auto tile_m0 = [&](int it) { int mt_, nt_; tm.get(blockIdx.x + it * gridDim.x, mt_, nt_); return mt_ * TM; };
-    float4 cur[HPC][4], nxt[HPC][4];
-    int it = 0, kc = 0, m0 = tile_m0(0);
-#pragma unroll
-    for (int h = 0; h < HPC; ++h) load_half(m0, h, cur[h]);
     const int total = n_my * chunks;
-    for (int q = 0; q < total; ++q) {
-      int nkc = kc + 1, nit = it, nm0 = m0;
-      if (nkc == chunks) { nkc = 0; nit = it + 1; }
-      if (q + 1 < total) {
-        if (nkc == 0) nm0 = tile_m0(nit);
+    auto load_chunk = [&](int q, float4 (&buf)[HPC][4]) {
+      const int it = q / chunks, kc = q - it * chunks;
+      const int m0 = tile_m0(it);
 #pragma unroll
-        for (int h = 0; h < HPC; ++h) load_half(nm0, nkc * HPC + h, nxt[h]);
-      }
+      for (int h = 0; h < HPC; ++h) load_half(m0, kc * HPC + h, buf[h]);
+    };
+    auto stage_chunk = [&](int q, float4 (&buf)[HPC][4]) {
       const int s = gc & 1;
       mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
       char* st = cv.stages + (size_t)s * STAGE_BYTES;
+      const int kc = q % chunks;
 #pragma unroll
-      for (int h = 0; h < HPC; ++h)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, cur[h][i]);
+      for (int h = 0; h < HPC; ++h) {
+        const bool second = g.div2 != 1.0f && (kc * HPC + h) * TKC + 4 * pc >= g.K1;      // columns of A2: exact division here,
+#pragma unroll                                                                              // not at load time (keeps the loads in flight)
+        for (int i = 0; i < 4; ++i) {
+          float4 x = buf[h][i];
+          if (second) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
+          store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
+        }
+      }
+      if (q + 2 < total) load_chunk(q + 2, buf);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->full_x[s]);
       ++gc;
-#pragma unroll
-      for (int h = 0; h < HPC; ++h)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cur[h][i] = nxt[h][i];
-      it = nit; kc = nkc; m0 = nm0;
+    };
+    float4 bufA[HPC][4], bufB[HPC][4];
+    load_chunk(0, bufA);
+    if (total > 1) load_chunk(1, bufB);
+    for (int q = 0; q < total; q += 2) {
+      stage_chunk(q, bufA);
+      if (q + 1 < total) stage_chunk(q + 1, bufB);
     }
     if (gprof && ptid == 0) atomicAdd(&g_tc_prof[19], (unsigned long long)(tc_clock() - p0));    // producers: all tiles of this CTA
   } else if (warp == MMA_WARP) {
