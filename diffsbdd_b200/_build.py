@@ -42,6 +42,8 @@ def build(force: bool = False, verbose: bool = False, instrumented: bool = False
     stamp = os.path.join(HERE, 'csrc', '.build_stamp_instr' if instrumented else '.build_stamp')
     lib_path = INSTR_LIB_PATH if instrumented else LIB_PATH
     extra = ['-DDSB_TC_INSTRUMENT=1'] if instrumented else []
+    if instrumented and os.environ.get('DSB_VARIANT_FLAGS'):      # tuning builds reuse the second library slot
+        extra = os.environ['DSB_VARIANT_FLAGS'].split()
     dig = _digest()
     if not force and os.path.exists(lib_path) and os.path.exists(stamp):
         with open(stamp) as f:

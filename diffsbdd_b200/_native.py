@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     'dsb_param_count', 'dsb_param_name', 'dsb_dynamics_create', 'dsb_dynamics_destroy',
     'dsb_edge_capacity', 'dsb_dynamics_workspace_bytes', 'dsb_dynamics_forward', 'dsb_dynamics_edges',
     'dsb_dynamics_last_launch_count', 'dsb_set_programmatic_launch', 'dsb_dynamics_set_math_mode', 'dsb_dynamics_set_profiling', 'dsb_dynamics_collect_profile',
-    'dsb_ddpm_ligand_update', 'dsb_last_error', 'dsb_version',
+    'dsb_ddpm_ligand_update', 'dsb_last_error', 'dsb_version', 'dsb_debug_set_tc_flags', 'dsb_debug_read_tc_prof',
 )
 
 
@@ -49,6 +49,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         return _LIB
     instr = os.environ.get('DSB_INSTRUMENT', '0') not in ('', '0')      # profiling tools only (profiles/tc_ablate.py)
     path = _build.INSTR_LIB_PATH if instr else _build.LIB_PATH
+    if os.environ.get('DSB_LIB_PATH'):                                  # tuning builds (profiles/build_variants.py)
+        path = os.environ['DSB_LIB_PATH']
     if not os.path.exists(path):
         if not build_if_missing:
             raise NativeError(f'{path} is missing: run `python -m diffsbdd_b200._build` (needs nvcc)')

@@ -348,6 +348,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 // =====================================================================================================
 // edge kernels
 // =====================================================================================================
+// unroll factors of the three hot loops (overridable for tuning builds: -DDSB_P_UNROLL=... etc.)
+#ifndef DSB_P_UNROLL
+#define DSB_P_UNROLL 1
+#endif
+#ifndef DSB_E1_UNROLL
+#define DSB_E1_UNROLL 1
+#endif
+#ifndef DSB_E2_UNROLL
+#define DSB_E2_UNROLL 1
+#endif
+constexpr int kPUnroll = DSB_P_UNROLL, kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
 constexpr int H256 = 256;
 constexpr int EPI_T_STRIDE = 36;          // 16-byte aligned rows: conflict-free row-wise STS.128 and column-wise LDS.32
 constexpr int NSCAL = 3;                   // scalar buffer sets (tile it uses set it % NSCAL)
@@ -474,7 +485,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       f32x2 s01 = pk2(0.f, 0.f), s23 = s01;      // four independent partial dot products
       const int edbg = tc_debug();
       long long ld_cyc = 0;
-#pragma unroll 1
+#pragma unroll kE1Unroll
       for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
         const long long l0 = prof_on ? tc_clock() : 0;
@@ -518,7 +529,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         const f32x2 gp = pk2(gate, gate);
         // pass 2: e = m * gate -> row-wise STS.128 into the per-warp buffer -> each lane reads its column (32 independent
         // LDS), sums 4-row chunks -> one RED per (chunk, column); REDs to the same receiver meet in L2
-#pragma unroll 1
+#pragma unroll kE2Unroll
         for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
           const long long l0 = prof_on ? tc_clock() : 0;
@@ -644,7 +655,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       for (int m = 0; m < nm; ++m) {
         const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H256;
         const size_t tb_off = has_tb ? (size_t)(a.tb[m] - a.tb[0]) : 0;
-#pragma unroll 2
+#pragma unroll kPUnroll
         for (int hf = 0; hf < halves; ++hf) {
           const int s = gc & 1;
           const bool same = hf + 1 < halves;

@@ -164,6 +164,14 @@ int dsb_ddpm_ligand_update(const float* z_lig, const float* eps_hat, const float
 const char* dsb_last_error(void);
 const char* dsb_version(void);
 
+/* ---- diagnostics of the tensor-core kernels (profiles/tc_ablate.py; no reference counterpart).  The product library is
+ * built without instrumentation: dsb_debug_set_tc_flags(flags != 0) returns -4 and the counters stay 0.  The instrumented
+ * build (-DDSB_TC_INSTRUMENT=1, libdiffsbdd_b200_instr.so) takes a bitmask that disables individual roles of the kernels
+ * (results are then garbage) and, with bit 512, accumulates in-kernel clock64 counters that dsb_debug_read_tc_prof copies
+ * into out64[64] and clears. */
+int dsb_debug_set_tc_flags(int flags);
+int dsb_debug_read_tc_prof(unsigned long long* out64);
+
 #ifdef __cplusplus
 }
 #endif
