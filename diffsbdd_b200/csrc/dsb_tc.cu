@@ -1,15 +1,17 @@
-// Tensor-core (tcgen05 / TMEM) kernels of the denoiser: 3xTF32 split products with fp32 accumulation in TMEM.
+// Tensor-core (tcgen05 / TMEM) kernels of the denoiser: 3-product split contractions (3xFP16 or 3xTF32 operands) with
+// fp32 accumulation in TMEM.
 //
-//   tc_node_gemm_kernel — C = act([A1 | A2/div] @ W + bias) (+R)        (node GEMMs: egnn_new.py:21-24, factorised W1a/W1b)
-//   tc_edge_gcl_kernel  — GCL.edge_model + receiver segment sum          (egnn_new.py:31-52)
-//   tc_edge_coord_kernel— EquivariantUpdate.coord_model                  (egnn_new.py:96-116)
+//   tc_node_gemm_kernel  — C = act([A1 | A2/div] @ W + bias) (+R)        (node GEMMs: egnn_new.py:21-24, factorised W1a/W1b)
+//   tc_edge_kernel<0,.>  — GCL.edge_model + receiver sums                 (egnn_new.py:31-52)
+//   tc_edge_kernel<1,.>  — EquivariantUpdate.coord_model                  (egnn_new.py:96-116)
 //
-// One persistent CTA per SM, 14 warps, warp-specialised (see dsb_tc.cuh):
-//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = one tile row), bias/SiLU/gate, segment sums, RED/STG
+// One persistent CTA per SM, warp-specialised (see dsb_tc.cuh):
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = one tile row), bias/SiLU/gate, 4-row chunk sums, RED/STG
 //   warps 4-11  producers: build the A operand chunk (gather Pa[row]+Pb[col]+radial terms, SiLU, hi/lo split) straight
 //               into 128B-swizzled shared memory; fence.proxy.async; arrive on full_x
-//   warp 12     MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 split terms) per 32-wide k-chunk
-//   warp 13     TMA issuer: cp.async.bulk of the pre-split, pre-swizzled weight chunk images (hi, lo) -> full_w
+//   warp 12     MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 split terms) per K-chunk
+//   warp 13     bulk-copy issuer: cp.async.bulk of the pre-split, pre-swizzled weight chunk images (hi, lo) -> full_w
+//   warps 14-15 (edge kernels only) scalar warps: per-edge indices, distances and directions one tile ahead
 // Two shared-memory stages (96 KB each) and two 256-column TMEM accumulators: the epilogue of tile t overlaps the
 // main loop of tile t+1.
 #include "dsb_tc.cuh"
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         c3 = tc_clock();
         atomicAdd(&g_tc_prof[0], (unsigned long long)(c1 - c0));   // epilogue: waiting for scalars/accumulator
         atomicAdd(&g_tc_prof[1], (unsigned long long)(c2 - c1));   // pass 1
-        atomicAdd(&g_tc_prof[2], (unsigned long long)(c3 - c2));   // pass 2 (GCL) / trans+segment sum (coord)
+        atomicAdd(&g_tc_prof[2], (unsigned long long)(c3 - c2));   // pass 2 (GCL) / trans + chunk sums (coord)
         atomicAdd(&g_tc_prof[3], 1ull);                            // virtual tiles
       }
       tc_fence_before();

@@ -43,7 +43,7 @@ with torch.no_grad():
         if flags & 512:
             c = read_prof()
             nt, npv = max(c[3], 1), max(c[13], 1)
-            print(f'   epilogue warp0 per virtual tile (cycles): wait {c[0] / nt:8.0f}  pass1 {c[1] / nt:8.0f}  pass2 {c[2] / nt:8.0f}   [TMEM ld: pass1 {c[4] / nt:7.0f} pass2 {c[5] / nt:7.0f}; pass2 scale+STS+syncwarp {c[6] / nt:7.0f}; wait::st {c[28] / nt:7.0f}; segment sums+RED {c[29] / nt:7.0f}]  (n={nt})')
+            print(f'   epilogue warp0 per virtual tile (cycles): wait {c[0] / nt:8.0f}  pass1 {c[1] / nt:8.0f}  pass2 {c[2] / nt:8.0f}   [TMEM ld: pass1 {c[4] / nt:7.0f} pass2 {c[5] / nt:7.0f}; pass2 scale+STS+syncwarp {c[6] / nt:7.0f}; wait::st {c[28] / nt:7.0f}; chunk sums+RED {c[29] / nt:7.0f}]  (n={nt})')
             print(f'   producer thread0 per virtual tile (cycles): tile-start {c[8] / npv:7.0f}  compute+gather {c[9] / npv:8.0f}  wait-empty {c[10] / npv:8.0f}  '
                   f'store {c[11] / npv:7.0f}  fence+arrive {c[12] / npv:7.0f}   (n={npv})')
         if flags & 512:
