@@ -573,11 +573,16 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
-      GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1, nullptr, 0, 0, 0};
-      DSB_TRY(gemm(g2, G.iW3));
-      GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0, ws.agg, H, 0, 0};
-      DSB_TRY(gemm(g3, G.iW4));
-      launches += 3;
+      if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !getenv("DSB_NO_FUSED_MLP")) {
+        DSB_TRY(launch_tc_node_mlp(dyn, dm, ws, G, f16, status, s));        // both layers in one kernel, hidden stays on chip
+        launches += 2;
+      } else {
+        GemmArgs g2 = {ws.h, H, H, ws.agg, H, H, c.normalization_factor, G.W3, H, G.b3, nullptr, 0, ws.hT, H, dm.N, H, 1, nullptr, 0, 0, 0};
+        DSB_TRY(gemm(g2, G.iW3));
+        GemmArgs g3 = {ws.hT, H, H, nullptr, 0, 0, 1.f, G.W4, H, G.b4, ws.h, H, ws.h, H, dm.N, H, 0, ws.agg, H, 0, 0};
+        DSB_TRY(gemm(g3, G.iW4));
+        launches += 3;
+      }
     }
     // one GEMM for everything that consumes the updated h: this block's coord/cross first layers and the next block's
     // edge first layer.  In conditional mode the receiver-side coord columns are needed for ligand rows only.

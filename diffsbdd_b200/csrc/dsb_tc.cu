@@ -19,6 +19,8 @@
 namespace dsb {
 using namespace tc;
 
+constexpr int H256 = 256;       // the tensor-core kernels are built for hidden_nf = 256
+
 // =====================================================================================================
 // weight images: B[n][k] (= the reference's own [out][in] Linear layout) split into hi/lo and laid out as
 // [n_tile][k_chunk][256 rows x 128 B, SWIZZLE_128B] so that one k-chunk is a single 32 KB bulk copy.
@@ -348,6 +350,222 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 }
 
 // =====================================================================================================
+// fused node MLP (egnn_new.py:48-58): h <- h + W4 SiLU(W3 [h | agg/norm] + b3) + b4 for one 128-row tile per CTA.
+// Phase 1 is the node GEMM above (producers build the A operand from h and agg, K = 2H, accumulator 0).  Its epilogue does
+// not go to global memory: the four epilogue warps apply bias + SiLU to the accumulator and write the result, already split
+// and swizzled, into the A slots of the stage ring, i.e. they ARE the producers of phase 2 (K = H, accumulator 1), whose
+// weight chunks the bulk-copy thread streams right behind those of phase 1.  The phase-2 epilogue adds bias and residual,
+// stores the new h in place (rows are private to the CTA) and re-arms the aggregate.  One launch and one [N,H] round trip
+// through global memory less than two node GEMMs.
+// =====================================================================================================
+struct TcMlpArgs {
+  const float* h; int ldh;                      // A1 of phase 1, residual of phase 2, output (in place)
+  const float* agg; int ldagg; float div;       // A2 of phase 1 (exact division), zeroed at the end
+  const float* W3hi; const float* W3lo;         // [1][2H/kc][8192] images
+  const float* W4hi; const float* W4lo;         // [1][H/kc][8192]
+  const float* b3; const float* b4;
+  float inv3, inv4;                             // 3xFP16: 1 / weight scale; 1 for 3xTF32
+  float* hout; float* zero; int M;
+  int32_t* status;
+};
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const Carve cv = carve_smem(smem_raw);
+  Control* ctl = cv.ctl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntm = (g.M + TM - 1) / TM;
+  const int n_my = ((int)blockIdx.x < ntm) ? (ntm - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (n_my == 0) return;
+  constexpr int KPC = F16 ? TKC16 : TKC;        // k-values per pipeline chunk
+  constexpr int CB_PER_CHUNK = KPC / 32;        // 32-column accumulator blocks per phase-2 chunk
+  constexpr int C1 = 2 * H256 / KPC, C2 = H256 / KPC, CT = C1 + C2;
+  constexpr int HPC = F16 ? 2 : 1;
+  pdl_trigger();
+  tc_begin(ctl, warp);
+  pdl_wait();
+
+  if (warp < EPI_WARPS) {
+    float* T = reinterpret_cast<float*>(cv.extra) + warp * (32 * GEMM_T_STRIDE);
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;
+    for (int it = 0; it < n_my; ++it) {
+      const int m0 = (blockIdx.x + it * gridDim.x) * TM;
+      const uint32_t tbase = ctl->tmem_base + ((uint32_t)(warp * 32) << 16);
+      // ---- phase-1 epilogue = phase-2 producer
+      mbar_wait(&ctl->acc_full[0], it & 1);
+      tc_fence_after();
+      const uint32_t q0 = (uint32_t)it * CT + C1;             // global index of the first phase-2 chunk
+      const int myrow = warp * 32 + lane;
+#pragma unroll 1
+      for (int cb = 0; cb < TN / 32; ++cb) {
+        const uint32_t q = q0 + cb / CB_PER_CHUNK;
+        const int s = q & 1;
+        if (cb % CB_PER_CHUNK == 0) mbar_wait(&ctl->empty[s], ((q >> 1) & 1) ^ 1);
+        char* st = cv.stages + (size_t)s * STAGE_BYTES;
+        float v[32];
+        tmem_ld32(tbase + cb * 32, v);
+        const f32x2 ip = pk2(g.inv3, g.inv3);
+#pragma unroll
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b3 + cb * 32 + 4 * p8));
+          f32x2 x01 = pk2(v[4 * p8], v[4 * p8 + 1]), x23 = pk2(v[4 * p8 + 2], v[4 * p8 + 3]);
+          if (F16) { x01 = fma2(x01, ip, pk2(bb.x, bb.y)); x23 = fma2(x23, ip, pk2(bb.z, bb.w)); }
+          else { x01 = add2(x01, pk2(bb.x, bb.y)); x23 = add2(x23, pk2(bb.z, bb.w)); }
+          x01 = silu2(x01); x23 = silu2(x23);
+          float4 x;
+          upk2(x01, x.x, x.y); upk2(x23, x.z, x.w);
+          store_piece<F16>(st, myrow, cb % CB_PER_CHUNK, p8, x);
+        }
+        if (cb % CB_PER_CHUNK == CB_PER_CHUNK - 1) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_n(&ctl->full_x[s], PROD_WARPS / EPI_WARPS);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->epi_done[0]);
+      // ---- phase-2 epilogue: h <- h + acc * inv4 + b4, aggregate re-armed
+      mbar_wait(&ctl->acc_full[1], it & 1);
+      tc_fence_after();
+      const uint32_t taddr = tbase + (uint32_t)TN;
+      auto load_res = [&](int cb, float4 (&rr)[8]) {
+        const int n = cb * 32 + tc4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = m0 + warp * 32 + 4 * i + tr;
+          rr[i] = row < g.M ? *reinterpret_cast<const float4*>(g.h + (size_t)row * g.ldh + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto do_block = [&](int cb, const float4 (&rr)[8]) {
+        const int n = cb * 32 + tc4;
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(g.b4 + n));
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const f32x2 ip = pk2(g.inv4, g.inv4), b01 = pk2(bias.x, bias.y), b23 = pk2(bias.z, bias.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + tr;
+          const int row = m0 + warp * 32 + rl;
+          const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+          if (row < g.M) {
+            f32x2 x01 = pk2(x.x, x.y), x23 = pk2(x.z, x.w);
+            if (F16) { x01 = fma2(x01, ip, b01); x23 = fma2(x23, ip, b23); }
+            else { x01 = add2(x01, b01); x23 = add2(x23, b23); }
+            x01 = add2(pk2(rr[i].x, rr[i].y), x01); x23 = add2(pk2(rr[i].z, rr[i].w), x23);
+            float4 o;
+            upk2(x01, o.x, o.y); upk2(x23, o.z, o.w);
+            *reinterpret_cast<float4*>(g.hout + (size_t)row * g.ldh + n) = o;
+            *reinterpret_cast<float4*>(g.zero + (size_t)row * g.ldagg + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        __syncwarp();
+      };
+      float4 ra[8], rb[8];
+      load_res(0, ra);
+#pragma unroll 1
+      for (int cb = 0; cb < TN / 32; cb += 2) {
+        load_res(cb + 1, rb);
+        do_block(cb, ra);
+        if (cb + 2 < TN / 32) load_res(cb + 2, ra);
+        do_block(cb + 1, rb);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->epi_done[1]);
+    }
+  } else if (warp < MMA_WARP) {
+    // producers: phase-1 chunks only (global chunk indices it*CT + kc, kc < C1); two register sets, loads two chunks ahead
+    const int ptid = threadIdx.x - EPI_WARPS * 32;
+    const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
+    const int total = n_my * C1;
+    auto load_chunk = [&](int j, float4 (&buf)[HPC][4]) {
+      const int it = j / C1, kc = j - it * C1;
+      const int m0 = (blockIdx.x + it * gridDim.x) * TM;
+#pragma unroll
+      for (int h = 0; h < HPC; ++h) {
+        const int k = (kc * HPC + h) * TKC + 4 * pc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + 16 * pw + 4 * sr + i;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < g.M) x = k < H256 ? *reinterpret_cast<const float4*>(g.h + (size_t)m * g.ldh + k)
+                                    : *reinterpret_cast<const float4*>(g.agg + (size_t)m * g.ldagg + (k - H256));
+          buf[h][i] = x;
+        }
+      }
+    };
+    auto stage_chunk = [&](int j, float4 (&buf)[HPC][4]) {
+      const int it = j / C1, kc = j - it * C1;
+      const uint32_t q = (uint32_t)it * CT + kc;
+      const int s = q & 1;
+      mbar_wait(&ctl->empty[s], ((q >> 1) & 1) ^ 1);
+      char* st = cv.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int h = 0; h < HPC; ++h) {
+        const bool second = (kc * HPC + h) * TKC + 4 * pc >= H256;       // aggregate columns: exact division by the normalisation
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 x = buf[h][i];
+          if (second) { x.x = __fdiv_rn(x.x, g.div); x.y = __fdiv_rn(x.y, g.div); x.z = __fdiv_rn(x.z, g.div); x.w = __fdiv_rn(x.w, g.div); }
+          store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
+        }
+      }
+      if (j + 2 < total) load_chunk(j + 2, buf);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+    };
+    float4 bufA[HPC][4], bufB[HPC][4];
+    load_chunk(0, bufA);
+    if (total > 1) load_chunk(1, bufB);
+    for (int j = 0; j < total; j += 2) {
+      stage_chunk(j, bufA);
+      if (j + 1 < total) stage_chunk(j + 1, bufB);
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (int it = 0; it < n_my; ++it) {
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(&ctl->epi_done[ph], (it & 1) ^ 1);        // accumulator ph drained by the epilogue of the previous tile
+          tc_fence_after();
+          const uint32_t d = ctl->tmem_base + (uint32_t)(ph * TN);
+          const int nchunks = ph == 0 ? C1 : C2;
+          for (int kc = 0; kc < nchunks; ++kc, ++q) {
+            const int s = q & 1;
+            const uint32_t par = (q >> 1) & 1;
+            mbar_wait(&ctl->full_w[s], par);
+            mbar_wait(&ctl->full_x[s], par);
+            tc_fence_after();
+            mma_issue_chunk<F16>(d, cv.stages + (size_t)s * STAGE_BYTES, kc == 0);
+            umma_commit(&ctl->empty[s]);
+          }
+          umma_commit(&ctl->acc_full[ph]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      uint32_t gc = 0;
+      for (int it = 0; it < n_my; ++it) {
+        tma_role(ctl, cv.stages, g.W3hi, g.W3lo, gc, C1);
+        tma_role(ctl, cv.stages, g.W4hi, g.W4lo, gc, C2);
+      }
+    }
+    __syncwarp();
+  }
+  tc_end(ctl, warp);
+}
+
+// =====================================================================================================
 // edge kernels
 // =====================================================================================================
 // unroll factors of the three hot loops (overridable for tuning builds: -DDSB_P_UNROLL=... etc.)
@@ -361,7 +579,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 #define DSB_E2_UNROLL 1
 #endif
 constexpr int kPUnroll = DSB_P_UNROLL, kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
-constexpr int H256 = 256;
 constexpr int EPI_T_STRIDE = 36;          // 16-byte aligned rows: conflict-free row-wise STS.128 and column-wise LDS.32
 constexpr int NSCAL = 3;                   // scalar buffer sets (tile it uses set it % NSCAL)
 constexpr int SCAL_WARPS = 2;              // warps 14, 15 of the edge kernels: per-edge scalars one tile ahead of the producers
@@ -769,6 +986,8 @@ static size_t gemm_smem_bytes() { return kTcSmemBase + sizeof(float) * EPI_WARPS
 static size_t edge_smem_bytes() { return kTcSmemBase + sizeof(EdgeExtra); }
 
 int configure_tc_kernels() {
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
   DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
   DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
   DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
@@ -799,6 +1018,22 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   const int n_tiles = dmt_ * ntn_ + (ntm_ - dmt_) * (ntn_ - a.dead_nt);
   const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
   DSB_CUDA_OK(launch_k(f16 ? tc_node_gemm_kernel<true> : tc_node_gemm_kernel<false>, grid, TC_THREADS, gemm_smem_bytes(), s, a));
+  return 0;
+}
+
+int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, bool f16, int32_t* status, cudaStream_t s) {
+  if (dm.N == 0) return 0;
+  TcMlpArgs a = {};
+  const int H = d->cfg.hidden_nf;
+  a.h = ws.h; a.ldh = H; a.agg = ws.agg; a.ldagg = H; a.div = d->cfg.normalization_factor;
+  a.W3hi = f16 ? w.iW3.h_hi : w.iW3.t_hi; a.W3lo = f16 ? w.iW3.h_lo : w.iW3.t_lo;
+  a.W4hi = f16 ? w.iW4.h_hi : w.iW4.t_hi; a.W4lo = f16 ? w.iW4.h_lo : w.iW4.t_lo;
+  a.b3 = w.b3; a.b4 = w.b4;
+  a.inv3 = f16 ? w.iW3.h_inv : 1.0f; a.inv4 = f16 ? w.iW4.h_inv : 1.0f;
+  a.hout = ws.h; a.zero = ws.agg; a.M = dm.N; a.status = status;
+  const int ntm = (dm.N + TM - 1) / TM;
+  const int grid = ntm < d->num_sms ? ntm : d->num_sms;
+  DSB_CUDA_OK(launch_k(f16 ? tc_node_mlp_kernel<true> : tc_node_mlp_kernel<false>, grid, TC_THREADS, gemm_smem_bytes(), s, a));
   return 0;
 }
 

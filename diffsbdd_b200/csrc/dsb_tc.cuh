@@ -54,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {       // one thread arriving for n participants
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -277,6 +280,26 @@ __device__ __forceinline__ int tc_debug() {
 // cycle accounting of one epilogue warp and one producer warp per CTA (enabled by g_tc_debug & 512; profiles/tc_ablate.py)
 __device__ unsigned long long g_tc_prof[64];
 __device__ __forceinline__ long long tc_clock() { return clock64(); }
+// the 12 MMAs of one K-chunk held in stage memory `st` (A_hi | A_lo | W_hi | W_lo): 4 k-steps x 3 split products into d
+template <bool F16>
+__device__ __forceinline__ void mma_issue_chunk(uint32_t d, char* st, bool first_chunk) {
+  const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte row (K=8 tf32 or K=16 fp16 each)
+    const uint32_t ko = ks * 32;
+    const uint32_t acc = (first_chunk && ks == 0) ? 0u : 1u;
+    if constexpr (F16) {
+      umma_f16(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, acc);
+      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_F16_M128_N256, 1u);
+      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, 1u);
+    } else {
+      umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, acc);
+      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
+      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
+    }
+  }
+}
+
 template <bool F16>
 __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile, int tag) {
   const uint32_t tmem = ctl->tmem_base;
@@ -302,22 +325,7 @@ __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_ti
       mbar_wait(&ctl->full_x[s], par);
       tc_fence_after();
       if (mprof) { q2 = tc_clock(); w_w += q1 - q0; w_x += q2 - q1; }
-      char* st = stages + (size_t)s * STAGE_BYTES;
-      const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
-      if (!skip)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte row (K=8 tf32 or K=16 fp16 each)
-        const uint32_t ko = ks * 32;
-        if constexpr (F16) {
-          umma_f16(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, (kc | ks) ? 1u : 0u);
-          umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_F16_M128_N256, 1u);
-          umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, 1u);
-        } else {
-          umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, (kc | ks) ? 1u : 0u);
-          umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
-          umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
-        }
-      }
+      if (!skip) mma_issue_chunk<F16>(d, stages + (size_t)s * STAGE_BYTES, kc == 0);
       umma_commit(&ctl->empty[s]);          // stage reusable once these MMAs have read it
       if (mprof) { q3 = tc_clock(); w_iss += q3 - q2; }
     }
