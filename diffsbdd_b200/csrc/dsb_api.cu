@@ -560,6 +560,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   const int nq = nm * 2 * H, ldP = nq + 2 * H, nrecv = nm * H;
   const PView pv_gcl = {ws.P + nq, ldP}, pv_coord = {ws.P, ldP};
   const bool conditional = dm.n_coord_rows < dm.N;
+  static const bool no_fused_mlp = getenv("DSB_NO_FUSED_MLP") != nullptr;      // A/B timing switch (two node GEMMs instead)
   for (int l = 0; l < c.n_layers; ++l) {
     for (int sub = 0; sub < c.inv_sublayers; ++sub) {
       const GclW& G = dyn->w.gcl[l][sub];
@@ -573,7 +574,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
-      if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !getenv("DSB_NO_FUSED_MLP")) {
+      if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !no_fused_mlp) {
         DSB_TRY(launch_tc_node_mlp(dyn, dm, ws, G, f16, status, s));        // both layers in one kernel, hidden stays on chip
         launches += 2;
       } else {
