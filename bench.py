@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the DiffSBDD denoising hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|reference-gpu]
+                    [--workload fullatom|ca|inpaint]
 
-metric : ligand atoms/s through the full 500-step DDPM sampling loop (501 denoiser calls), batch of 64
-         synthetic pocket+ligand graphs per GPU (N_L=25, N_P=175 -> N=200), crossdock_fullatom_cond dims.
-step   : ONE complete ``ConditionalDDPM.sample_given_pocket`` of the per-GPU batch.
-value  : whole-job atoms/s with the pocket already resident in HBM (CUDA events, max over ranks).
-e2e    : same metric through the public API (``LigandPocketDDPM.generate_ligand_tensors``) from pinned
-         HOST buffers, host->device copy of the pocket and device->host read of the ligands inside the timed
-         region.
---impl reference : the reference's CPU implementation of the path (oracle port — /root/reference cannot travel
-         to the GPU box), all host threads, bounded sample per step, extrapolated linearly to 501 calls.
+metric : ligand atoms/s through the full DDPM sampling loop of the per-GPU batch.
+workload (BASELINE.json configs):
+  fullatom  configs[2] (default; configs[3] under torchrun): crossdock_fullatom_cond dims, 500 steps, batch 64/GPU,
+            N_L=25, N_P=175 (rho 0.045 A^-3)                      -> 501 denoiser calls per step
+  ca        configs[1]: crossdock_ca_cond dims, 500 steps, batch 32, N_L=25, N_P=40 (rho 0.007 A^-3)
+  inpaint   configs[4]: ConditionalDDPM.inpaint, full-atom dims, batch 64, 10 of 25 ligand atoms fixed, center='ligand';
+            schedule --inpaint-timesteps x --resamplings (script default 50 x 20, inpaint.py:205-206; also 500 x 1)
+step   : ONE complete sampling run (``sample_given_pocket`` / ``inpaint``) of the per-GPU batch.
+value  : whole-job atoms/s with the inputs already resident in HBM (CUDA events, max over ranks).
+e2e    : same metric through the public API from pinned HOST buffers, host->device copies of the inputs and the
+         device->host read of the ligands inside the timed region.
+--impl reference     : the reference's CPU implementation of the path (oracle port — /root/reference cannot travel to the
+                       GPU box), all host threads it can use, bounded sample per step, extrapolated linearly.
+--impl reference-gpu : the same ATen op sequence as the reference on the B200 (device='cuda', eager, reference-order DDPM
+                       loop): the fair "beat this" number of SURVEY.md §8(d); bounded sample, extrapolated linearly.
 """
 from __future__ import annotations
 
@@ -35,35 +42,69 @@ import torch  # noqa: E402
 METRIC = 'ligand_atoms_per_sec_500step_ddpm'
 UNIT = 'ligand atoms/s'
 
+WORKLOADS = {
+    # name: (BASELINE.json config index, batch, n_lig, n_pocket, density, norm_values, yml, full-atom?)
+    'fullatom': (2, 64, 25, 175, 0.045, (1, 4), 'crossdock_fullatom_cond', True),
+    'ca': (1, 32, 25, 40, 0.007, (1, 1), 'crossdock_ca_cond', False),
+    'inpaint': (4, 64, 25, 175, 0.045, (1, 4), 'crossdock_fullatom_cond', True),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=64, help='pockets per GPU')
-    ap.add_argument('--n-lig', type=int, default=25)
-    ap.add_argument('--n-pocket', type=int, default=175)
-    ap.add_argument('--timesteps', type=int, default=500)
-    ap.add_argument('--workload', default='fullatom', choices=['fullatom', 'ca'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-gpu'])
+    ap.add_argument('--workload', default='fullatom', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=None, help='pockets per GPU (default: the workload\'s)')
+    ap.add_argument('--n-lig', type=int, default=None)
+    ap.add_argument('--n-pocket', type=int, default=None)
+    ap.add_argument('--timesteps', type=int, default=500, help='diffusion steps T of the model / sampling run')
+    ap.add_argument('--inpaint-timesteps', type=int, default=50, help='inpaint: sub-sampled steps (inpaint.py:206)')
+    ap.add_argument('--resamplings', type=int, default=20, help='inpaint: RePaint resamplings (inpaint.py:205)')
+    ap.add_argument('--n-fixed', type=int, default=10, help='inpaint: fixed ligand atoms per sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--profile-calls', type=int, default=10)
     ap.add_argument('--cpu-sample-seconds', type=float, default=20.0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    _, b, nl, npk, _, _, _, _ = WORKLOADS[args.workload]
+    args.batch = b if args.batch is None else args.batch
+    args.n_lig = nl if args.n_lig is None else args.n_lig
+    args.n_pocket = npk if args.n_pocket is None else args.n_pocket
+    return args
 
 
 def workload(args):
     from diffsbdd_b200.config import FULLATOM_COND, CA_COND
-    if args.workload == 'fullatom':
-        return FULLATOM_COND, 0.045, (1, 4), 'crossdock_fullatom_cond'
-    return CA_COND, 0.007, (1, 1), 'crossdock_ca_cond'
+    _, _, _, _, density, norm_values, yml, fullatom = WORKLOADS[args.workload]
+    return (FULLATOM_COND if fullatom else CA_COND), density, norm_values, yml
 
 
-def workload_name(args, yml):
-    return (f'BASELINE configs[2]: conditional {args.workload} model ({yml}.yml dims), {args.timesteps}-step DDPM, '
-            f'batch {args.batch}/GPU, N_L={args.n_lig}, N_P={args.n_pocket}')
+def denoiser_calls(args):
+    """Denoiser calls of one step (one sampling run)."""
+    if args.workload == 'inpaint':
+        return args.inpaint_timesteps * args.resamplings + 1
+    return args.timesteps + 1
+
+
+def workload_config(args, world=1):
+    """The `config` object of the JSON line: identical keys and values in every arm (b200 / reference / reference-gpu)."""
+    idx, _, _, _, density, _, yml, _ = WORKLOADS[args.workload]
+    if args.workload == 'fullatom' and world > 1:
+        idx = 3
+    name = {1: 'conditional C-alpha model', 2: 'conditional full-atom model', 3: 'conditional full-atom model, batch split over GPUs',
+            4: 'inpainting (ConditionalDDPM.inpaint, fixed-atom mask + resampling), full-atom model'}[idx]
+    cfg = {'workload': (f'BASELINE configs[{idx}]: {name} ({yml}.yml dims), batch {args.batch}/GPU, N_L={args.n_lig}, '
+                        f'N_P={args.n_pocket}'),
+           'baseline_config_index': idx, 'global_batch': args.batch * world, 'batch_per_gpu': args.batch,
+           'n_lig': args.n_lig, 'n_pocket': args.n_pocket, 'pocket_density_per_A3': density,
+           'timesteps': args.timesteps, 'denoiser_calls_per_step': denoiser_calls(args)}
+    if args.workload == 'inpaint':
+        cfg.update({'inpaint_timesteps': args.inpaint_timesteps, 'resamplings': args.resamplings, 'n_fixed': args.n_fixed,
+                    'center': 'ligand'})
+    return cfg
 
 
 def hparams(cfg, args, norm_values):
@@ -81,7 +122,22 @@ def hparams(cfg, args, norm_values):
                 diffusion_params=diff, num_workers=0, augment_noise=0, augment_rotation=False, clip_grad=True,
                 eval_epochs=1, eval_params=Namespace(), visualize_sample_epoch=1, visualize_chain_epoch=1,
                 auxiliary_loss=False, loss_params=Namespace(), mode='pocket_conditioning', node_histogram=hist,
-                pocket_representation='full-atom' if args.workload == 'fullatom' else 'CA')
+                pocket_representation='full-atom' if WORKLOADS[args.workload][7] else 'CA')
+
+
+def inpaint_inputs(cfg, args, n_graphs, seed, device='cpu'):
+    """per sample the first n_fixed of the N_L ligand atoms are known (inpaint.py:117-141),
+    known coordinates ~ N(0, 1.5^2 A) around the pocket COM (the synthetic pockets are centred), random one-hot types."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    n = n_graphs * args.n_lig
+    x = torch.randn((n, 3), generator=g) * 1.5
+    types = torch.randint(0, cfg.atom_nf, (n,), generator=g)
+    fixed = torch.zeros(n)
+    fixed.view(n_graphs, args.n_lig)[:, :args.n_fixed] = 1
+    lig = {'x': x, 'one_hot': torch.nn.functional.one_hot(types, cfg.atom_nf).float(),
+           'size': torch.full((n_graphs,), args.n_lig, dtype=torch.int64),
+           'mask': torch.repeat_interleave(torch.arange(n_graphs), args.n_lig)}
+    return {k: v.to(device) for k, v in lig.items()}, fixed.to(device)
 
 
 # ---- clocks sampler (B200_PROFILING.md "clocks DURING the timed region") -------------------------------------
@@ -105,6 +161,7 @@ class ClockSampler:
         except Exception:
             self.proc = None
             return
+
         def pump():
             for line in self.proc.stdout:
                 self.rows.append(line.strip())
@@ -142,41 +199,56 @@ def l2_flush(buf):
     buf.add_(1.0)    # read+write 256 MiB > 126 MB L2
 
 
-# ---- CPU baseline: oracle port of the reference's PyTorch path on the host cores -------------------------------
-def cpu_reference_sample(args, budget_s, rank_seed=0, sub_batch=8):
-    """Times the CPU port on a BOUNDED sample of the same workload: the first ``sub_batch`` pockets of the batch
-    (CPU cost is linear in the number of pockets: graphs are independent), 1 reverse step + the final p(x|z0) call
-    repeated until ~budget_s; atoms/s extrapolated to the full 501-call loop (every reverse step has the same cost).
-    The torch thread count is calibrated first (all host cores are offered; the fastest setting is used)."""
+# ---- reference arms: the oracle port of the reference's PyTorch path, on the host cores or eager on the GPU -----------
+def _reference_ddpm(args, device):
     from diffsbdd_b200 import synthetic as syn
     from diffsbdd_b200.conditional_model import ConditionalDDPM
     from oracle.cpu_denoiser import OracleDynamics
     cfg, density, norm_values, yml = workload(args)
-    cores = os.cpu_count() or 1
     sd = syn.synthetic_state_dict(cfg, 0)
-    dyn = OracleDynamics(cfg, sd)
+    dyn = OracleDynamics(cfg, sd, device=device)
     hist = np.ones((args.n_lig + 2, args.n_pocket + 2)).tolist()
     ddpm = ConditionalDDPM(dynamics=dyn, atom_nf=cfg.atom_nf, residue_nf=cfg.residue_nf, n_dims=3,
                            timesteps=args.timesteps, noise_schedule='polynomial_2', noise_precision=5e-4,
                            loss_type='l2', norm_values=norm_values, size_histogram=hist)
-    ddpm.eval()
-    nb = min(sub_batch, args.batch)
-    pocket = syn.synthetic_pocket(cfg, [args.n_pocket] * nb, seed=3 + rank_seed, density=density)
-    n_lig = torch.full((nb,), args.n_lig, dtype=torch.int64)
+    ddpm.loop_engine = 'eager'          # the reference's own loop: same torch ops, same order, per-step host syncs
+    return ddpm.to(device).eval(), dyn, cfg, density
+
+
+def _reference_run(args, ddpm, cfg, density, nb, sub_steps, device, seed=3):
+    """One bounded sample: ``sub_steps`` reverse steps (+ the final p(x|z0) call) of the workload's sampler on the first
+    ``nb`` pockets.  Returns seconds."""
+    from diffsbdd_b200 import synthetic as syn
+    pocket = syn.synthetic_pocket(cfg, [args.n_pocket] * nb, seed=seed, density=density)
+    pocket = {k: v.to(device) for k, v in pocket.items()}
+    t0 = time.perf_counter()
+    if args.workload == 'inpaint':
+        lig, fixed = inpaint_inputs(cfg, args, nb, seed, device)
+        ddpm.inpaint(lig, pocket, fixed, resamplings=1, timesteps=sub_steps, center='ligand')
+    else:
+        ddpm.sample_given_pocket(pocket, torch.full((nb,), args.n_lig, dtype=torch.int64, device=device), timesteps=sub_steps)
+    if torch.device(device).type == 'cuda':
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+def cpu_reference_sample(args, budget_s, sub_batch=None):
+    """Times the CPU port on a BOUNDED sample of the same workload: the first ``nb`` pockets of the batch (CPU cost is
+    linear in the number of pockets: graphs are independent), 1 reverse step + the final p(x|z0) call, repeated until
+    ~budget_s; atoms/s extrapolated to the full loop (every denoiser call of the loop has the same cost; the O(N)
+    update/blend ops between calls are <1 % of a call on the CPU).  The torch thread count is calibrated first."""
+    ddpm, dyn, cfg, density = _reference_ddpm(args, 'cpu')
+    cores = os.cpu_count() or 1
+    nb = min(sub_batch or 8, args.batch)
     torch.manual_seed(0)
-
-    def one_sample():
-        t0 = time.perf_counter()
-        ddpm.sample_given_pocket(dict(pocket), n_lig, timesteps=1)      # 2 denoiser calls
-        return time.perf_counter() - t0
-
+    one = lambda: _reference_run(args, ddpm, cfg, density, nb, 1, 'cpu')      # 2 denoiser calls
     best_threads, best_t = cores, None
     cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
     t_cal0 = time.perf_counter()
     for th in cands:
         torch.set_num_threads(th)
-        one_sample()
-        t = one_sample()
+        one()
+        t = one()
         if best_t is None or t < best_t:
             best_threads, best_t = th, t
         if time.perf_counter() - t_cal0 > budget_s:
@@ -186,27 +258,26 @@ def cpu_reference_sample(args, budget_s, rank_seed=0, sub_batch=8):
     t0 = time.perf_counter()
     reps = 0
     while reps < 1 or (time.perf_counter() - t0 < 0.5 * budget_s and reps < 50):
-        one_sample()
+        one()
         reps += 1
     dt = time.perf_counter() - t0
     per_call = dt / dyn.calls
-    full = per_call * (args.timesteps + 1)
+    n_calls = denoiser_calls(args)
     atoms = nb * args.n_lig
-    return {'value': atoms / full, 'unit': UNIT, 'cores': best_threads, 'kind': 'port',
+    return {'value': atoms / (per_call * n_calls), 'unit': UNIT, 'cores': best_threads, 'kind': 'port',
             'sample': (f'oracle port of the reference PyTorch path (oracle/egnn_oracle.py + eager reference-order DDPM '
                        f'loop) on the first {nb} of the {args.batch} pockets, {dyn.calls} denoiser calls in {dt:.1f} s = '
-                       f'{per_call:.2f} s/call, extrapolated x{args.timesteps + 1} calls; torch threads calibrated over '
+                       f'{per_call:.2f} s/call, extrapolated x{n_calls} calls; torch threads calibrated over '
                        f'{cands} of {cores} host cores -> {best_threads}'),
-            'seconds_per_denoiser_call': per_call, 'host_cores': cores, 'torch_threads': best_threads}, dt, dyn.calls
+            'seconds_per_denoiser_call': per_call, 'host_cores': cores, 'torch_threads': best_threads,
+            'sample_pockets': nb}, dt, dyn.calls
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    _, _, _, yml = workload(args)
-    times = []
-    base = None
+    times, base = [], None
     per_step_budget = max(4.0, min(args.cpu_sample_seconds, 120.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
         base, dt, calls = cpu_reference_sample(args, per_step_budget)
@@ -214,12 +285,47 @@ def run_reference(args):
             times.append(dt)
         if i == 0 and args.warmup + args.steps > 1 and dt * (args.warmup + args.steps) > 240:
             per_step_budget = max(2.0, per_step_budget / 2)
+    cfgj = workload_config(args)
+    cfgj['reference_sample'] = 'bounded sample per step, extrapolated: ' + base['sample']
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * statistics.mean(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args, yml), 'step': 'bounded sample: ' + base['sample']},
-            'cpu_baseline': base,
+            'config': cfgj, 'cpu_baseline': base,
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args):
+    """The reference's op sequence (oracle port, device='cuda') inside the reference-order eager loop on ONE B200, full
+    batch: ``sub`` reverse steps + the final call per timed step, extrapolated to the full loop."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({'impl': 'reference-gpu', 'unavailable': 'no CUDA device'}))
+        return
+    device = 'cuda:0'
+    ddpm, dyn, cfg, density = _reference_ddpm(args, device)
+    sub = 20
+    torch.manual_seed(0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _reference_run(args, ddpm, cfg, density, args.batch, 2, device)
+    dyn.calls = 0
+    sampler = ClockSampler(torch.device(device))
+    sampler.start()
+    times = [_reference_run(args, ddpm, cfg, density, args.batch, sub, device) for _ in range(max(1, min(args.steps, 5)))]
+    clocks = sampler.stop()
+    per_call = sum(times) / dyn.calls
+    n_calls = denoiser_calls(args)
+    value = args.batch * args.n_lig / (per_call * n_calls)
+    cfgj = workload_config(args)
+    cfgj['reference_sample'] = (f'full batch of {args.batch} pockets, {dyn.calls} denoiser calls in {sum(times):.2f} s = '
+                                f'{1e3 * per_call:.1f} ms/call (eager ATen ops incl. per-step host syncs), extrapolated x{n_calls} calls')
+    line = {'impl': 'reference-gpu', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': len(times),
+            'warmup': args.warmup, 'ms_per_step': 1e3 * per_call * n_calls, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfgj, 'clocks': clocks,
+            'ms_per_denoiser_call': 1e3 * per_call,
+            'note': 'oracle/egnn_oracle.py restates the reference op for op (bit-identical on CPU); this is that op sequence on cuda:0'}
     print(json.dumps(line), flush=True)
 
 
@@ -227,6 +333,7 @@ def run_reference(args):
 def run_b200(args):
     import torch.distributed as dist
     from diffsbdd_b200 import synthetic as syn
+    from diffsbdd_b200.distributed import sample_given_pocket_sharded, shard_bounds, shard_pocket
     from diffsbdd_b200.lightning_modules import LigandPocketDDPM
 
     rank = int(os.environ.get('RANK', '0'))
@@ -247,37 +354,60 @@ def run_b200(args):
     model.to(device).eval()
     ddpm, dyn = model.ddpm, model.ddpm.dynamics
     B, NL, NP, T = args.batch, args.n_lig, args.n_pocket, args.timesteps
+    inpaint = args.workload == 'inpaint'
 
-    pocket_host = syn.synthetic_pocket(cfg, [NP] * B, seed=3 + rank, density=density)
-    pocket_host = {k: v.pin_memory() for k, v in pocket_host.items()}
+    # the WHOLE job (B pockets per rank, weak scaling) is described on every rank; each rank samples its contiguous shard
+    # (diffsbdd_b200.distributed).  Shard r of the job is the batch seeded 3 + r.
+    parts = [syn.synthetic_pocket(cfg, [NP] * B, seed=3 + r, density=density) for r in range(world)]
+    job = {'x': torch.cat([p['x'] for p in parts]), 'one_hot': torch.cat([p['one_hot'] for p in parts]),
+           'size': torch.cat([p['size'] for p in parts]),
+           'mask': torch.cat([p['mask'] + r * B for r, p in enumerate(parts)])}
+    job_dev = {k: v.to(device) for k, v in job.items()}
+    n_lig_job = torch.full((B * world,), NL, dtype=torch.int64, device=device)
+    lo, hi = shard_bounds(B * world, world, rank)
+    pocket_host = {k: v.contiguous().pin_memory() for k, v in shard_pocket(job, lo, hi).items()}
     pocket_dev = {k: v.to(device) for k, v in pocket_host.items()}
     n_lig_host = torch.full((B,), NL, dtype=torch.int64).pin_memory()
-    n_lig_dev = n_lig_host.to(device)
+    lig_host = fixed_host = lig_dev = fixed_dev = None
+    if inpaint:
+        lig_host, fixed_host = inpaint_inputs(cfg, args, B, 3 + rank)
+        lig_host = {k: v.pin_memory() for k, v in lig_host.items()}
+        fixed_host = fixed_host.pin_memory()
+        lig_dev = {k: v.to(device) for k, v in lig_host.items()}
+        fixed_dev = fixed_host.to(device)
     flush_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=device)
     torch.manual_seed(1234 + rank)
+    step_no = [0]
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(device)
 
-    gathered = [None]
-
     def step_device():
-        xh_lig, _, lig_mask, _ = ddpm.sample_given_pocket(dict(pocket_dev), n_lig_dev, timesteps=T)
-        if world > 1:   # the only collective of the path — final gather of the ligands
-            outs = [torch.empty_like(xh_lig) for _ in range(world)]
-            dist.all_gather(outs, xh_lig.contiguous())
-            gathered[0] = outs
-        return xh_lig
+        step_no[0] += 1
+        if inpaint:
+            xh_lig, _, _, _ = ddpm.inpaint({k: v.clone() for k, v in lig_dev.items()}, dict(pocket_dev), fixed_dev,
+                                           resamplings=args.resamplings, timesteps=args.inpaint_timesteps, center='ligand')
+            return xh_lig
+        # library path: this rank's shard + the final all_gather of the ligands (the only collective of the path)
+        xh_all, _, _ = sample_given_pocket_sharded(ddpm, dict(job_dev), n_lig_job, base_seed=1000 * step_no[0], timesteps=T)
+        return xh_all
 
     def step_e2e():
         pocket = {k: v.to(device, non_blocking=True) for k, v in pocket_host.items()}
-        n_lig = n_lig_host.to(device, non_blocking=True)
-        xh_lig, _, lig_mask, _ = model.generate_ligand_tensors(pocket, n_lig, timesteps=T)
+        if inpaint:
+            lig = {k: v.to(device, non_blocking=True) for k, v in lig_host.items()}
+            fixed = fixed_host.to(device, non_blocking=True)
+            xh_lig, _, lig_mask, _ = ddpm.inpaint(lig, pocket, fixed, resamplings=args.resamplings,
+                                                  timesteps=args.inpaint_timesteps, center='ligand')
+        else:
+            n_lig = n_lig_host.to(device, non_blocking=True)
+            xh_lig, _, lig_mask, _ = model.generate_ligand_tensors(pocket, n_lig, timesteps=T)
         return xh_lig.cpu(), lig_mask.cpu()
 
     def timed(fn, k):
+        """k steps between two events; returns (max over ranks of the total ms, per-rank total ms list)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -287,16 +417,19 @@ def run_b200(args):
         e1.record()
         torch.cuda.synchronize(device)
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        per_rank = [float(ms.item())]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            allms = [torch.empty_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank = [float(m.item()) for m in allms]
         barrier()
-        return float(ms.item())
+        return max(per_rank), per_rank
 
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(device)
     sampler.start()
-    ms_total = timed(step_device, args.steps)
+    ms_total, per_rank_ms = timed(step_device, args.steps)
     clocks = sampler.stop()
     e_last = dyn.last_num_edges
     atoms_per_step = B * NL * world
@@ -306,15 +439,22 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
-        h2d = sum(v.numel() * v.element_size() for v in pocket_host.values()) + n_lig_host.numel() * 8
+        ms_e2e, _ = timed(step_e2e, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in pocket_host.values())
+        if inpaint:
+            h2d += sum(v.numel() * v.element_size() for v in lig_host.values()) + fixed_host.numel() * 4
+            api = 'ConditionalDDPM.inpaint(ligand, pocket, lig_fixed [pinned host]->device, ...) -> .cpu()  (inpaint.py:147)'
+        else:
+            h2d += n_lig_host.numel() * 8
+            api = 'LigandPocketDDPM.generate_ligand_tensors(pocket[pinned host]->device, ...) -> .cpu()'
         d2h = B * NL * (3 + cfg.atom_nf) * 4 + B * NL * 8
         e2e = {'value': atoms_per_step * args.steps / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-               'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
-               'api': 'LigandPocketDDPM.generate_ligand_tensors(pocket[pinned host]->device, ...) -> .cpu()'}
+               'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps, 'api': api}
 
     launches_fwd = dyn.launches_per_forward
-    gpu_launches = args.steps * ((T + 1) * launches_fwd + T)     # + one fused DDPM update kernel per reverse step
+    n_calls = denoiser_calls(args)
+    per_iter_extra = 2 if inpaint else 1      # fused DDPM update (+ fused RePaint iteration) per reverse step
+    gpu_launches = args.steps * (n_calls * launches_fwd + (n_calls - 1) * per_iter_extra)
 
     # ---- live kernel timing for the roofline: eager forwards with CUDA events on the launch stream ------------
     roof = roof32 = kernel_ms = None
@@ -355,20 +495,22 @@ def run_b200(args):
             hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
             tens_peak = float(peaks.get('bf16_tflops', 1590.0))
             src = 'MEASURED_PEAKS.json (of measured)' if peaks else 'B200_PROFILING.md fallback (of fallback)'
-            traffic, traffic_src = None, None
+            traffic, traffic_src, traffic_edges = None, None, None
             try:   # DRAM bytes per launch from the committed ncu --set full capture (never measured under the profiler here)
                 with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
-                    tr = json.load(f).get(kname)
+                    tj = json.load(f)
+                tr = tj.get(f'{kname}@{args.workload}') or tj.get(kname)
                 if tr:
-                    traffic, traffic_src = tr['dram_bytes_per_launch'], tr['source']
+                    traffic, traffic_src, traffic_edges = tr['dram_bytes_per_launch'], tr['source'], tr.get('edges')
             except Exception:
                 pass
             ach_b = alg_bytes / (gcl_ms * 1e-3) / 1e9
             ach_f = alg_flops / (gcl_ms * 1e-3) / 1e12
             smax = (clocks.get('sm_max_mhz') or 1965.0)
             fp32_peak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * 2 * smax * 1e6 / 1e12
-            common = {'kernel': kname, 'avg_launch_ms': gcl_ms, 'edges': E, 'traffic': traffic, 'traffic_source': traffic_src,
-                      'algorithmic_bytes_per_launch': alg_bytes, 'algorithmic_flops_per_launch': alg_flops}
+            common = {'kernel': kname, 'avg_launch_ms': gcl_ms, 'edges': E, 'traffic': traffic, 'traffic_edges': traffic_edges,
+                      'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': alg_bytes,
+                      'algorithmic_flops_per_launch': alg_flops}
             if tensor_path:
                 # the contraction runs on the tensor pipe as 3 split products: executed tensor FLOPs = 3 x algorithmic
                 roof = dict(common, bound='tensor', achieved=ach_f, peak=tens_peak, unit='TFLOP/s', frac=ach_f / tens_peak,
@@ -393,18 +535,31 @@ def run_b200(args):
         cpu_base, _, _ = cpu_reference_sample(args, args.cpu_sample_seconds)
 
     if rank == 0:
+        cfgj = workload_config(args, world)
+        engine = 'eager'
+        if ddpm._graph_cache:
+            engine = ('cuda_graph replay: denoiser + fused reverse update + fused RePaint iteration per (s, u)' if inpaint
+                      else 'cuda_graph replay of one reverse step')
+        cfgj.update({'arithmetic': {0: 'fp32 FFMA', 7: '3xTF32 tcgen05', 15: '3xFP16 tcgen05'}.get(dyn.math_mode, str(dyn.math_mode)),
+                     'edges_last_call': e_last,
+                     'parallelism': f'dp{world} (contiguous pocket shards per rank via diffsbdd_b200.distributed, no collective '
+                                    'inside the loop, final all_gather of the ligands)',
+                     'l2': '256 MiB read+write flush before every timed step', 'loop_engine': engine,
+                     'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py)'})
+        per_rank_step = [m / args.steps for m in per_rank_ms]
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': workload_name(args, yml), 'arithmetic': {0: 'fp32 FFMA', 7: '3xTF32 tcgen05', 15: '3xFP16 tcgen05'}.get(dyn.math_mode, str(dyn.math_mode)), 'global_batch': B * world, 'batch_per_gpu': B,
-                           'n_lig': NL, 'n_pocket': NP, 'timesteps': T, 'denoiser_calls_per_step': T + 1,
-                           'edges_last_call': e_last, 'parallelism': f'dp{world} (independent pockets per rank, '
-                           'final all_gather of ligands)', 'l2': '256 MiB read+write flush before every timed step',
-                           'loop_engine': 'cuda_graph replay of one reverse step' if ddpm._graph_cache else 'eager',
-                           'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py)'},
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfgj,
+                'ms_per_step_by_rank': {'min': min(per_rank_step), 'median': statistics.median(per_rank_step),
+                                        'max': max(per_rank_step)},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': gpu_launches,
                 'launches_per_denoiser_call': launches_fwd, 'math_mode': dyn.math_mode, 'roofline': roof, 'roofline_secondary': roof32,
                 'kernel_ms_per_denoiser_call': kernel_ms, 'cpu_baseline': cpu_base}
+        if inpaint:
+            gen = (NL - args.n_fixed) / NL
+            line['generated_atoms_per_s'] = value * gen        # atoms actually generated (N_L - n_fixed per sample)
+            if e2e:
+                e2e['generated_atoms_per_s'] = e2e['value'] * gen
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -414,6 +569,8 @@ def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'reference-gpu':
+        run_reference_gpu(args)
     else:
         run_b200(args)
 

@@ -36,6 +36,18 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def is_current(instrumented: bool = False) -> bool:
+    """True when the library on disk was built from exactly the sources (and flags) next to it."""
+    stamp = os.path.join(HERE, 'csrc', '.build_stamp_instr' if instrumented else '.build_stamp')
+    lib_path = INSTR_LIB_PATH if instrumented else LIB_PATH
+    if instrumented and os.environ.get('DSB_VARIANT_FLAGS'):
+        return os.path.exists(lib_path)
+    if not (os.path.exists(lib_path) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as f:
+        return f.read().strip() == _digest()
+
+
 def build(force: bool = False, verbose: bool = False, instrumented: bool = False) -> str:
     """Compile every CUDA translation unit for sm_100a and link the shared library. Returns its path.
     instrumented=True builds the ablation / cycle-accounting variant next to the product library."""

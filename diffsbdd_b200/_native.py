@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     'dsb_param_count', 'dsb_param_name', 'dsb_dynamics_create', 'dsb_dynamics_destroy',
     'dsb_edge_capacity', 'dsb_dynamics_workspace_bytes', 'dsb_dynamics_forward', 'dsb_dynamics_edges',
     'dsb_dynamics_last_launch_count', 'dsb_set_programmatic_launch', 'dsb_dynamics_set_math_mode', 'dsb_dynamics_set_profiling', 'dsb_dynamics_collect_profile',
-    'dsb_ddpm_ligand_update', 'dsb_last_error', 'dsb_version', 'dsb_debug_set_tc_flags', 'dsb_debug_read_tc_prof',
+    'dsb_ddpm_ligand_update', 'dsb_ddpm_inpaint_update', 'dsb_last_error', 'dsb_version', 'dsb_debug_set_tc_flags', 'dsb_debug_read_tc_prof',
 )
 
 
@@ -51,9 +51,14 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     path = _build.INSTR_LIB_PATH if instr else _build.LIB_PATH
     if os.environ.get('DSB_LIB_PATH'):                                  # tuning builds (profiles/build_variants.py)
         path = os.environ['DSB_LIB_PATH']
-    if not os.path.exists(path):
+    if os.environ.get('DSB_LIB_PATH'):
+        if not os.path.exists(path):
+            raise NativeError(f'DSB_LIB_PATH={path} does not exist')
+    elif not os.path.exists(path) or not _build.is_current(instrumented=instr):
+        # missing, or built from other sources than the ones next to it (the .so is git-ignored and travels separately):
+        # a stale library behind fixed ctypes signatures would corrupt memory silently
         if not build_if_missing:
-            raise NativeError(f'{path} is missing: run `python -m diffsbdd_b200._build` (needs nvcc)')
+            raise NativeError(f'{path} is missing or stale: run `python -m diffsbdd_b200._build` (needs nvcc)')
         _build.build(instrumented=instr)
     lib = C.CDLL(path)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
@@ -88,6 +93,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.dsb_dynamics_collect_profile.restype = C.c_int
     lib.dsb_ddpm_ligand_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp]
     lib.dsb_ddpm_ligand_update.restype = C.c_int
+    lib.dsb_ddpm_inpaint_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
+    lib.dsb_ddpm_inpaint_update.restype = C.c_int
     _LIB = lib
     return lib
 

@@ -109,7 +109,7 @@ class ConditionalDDPM(EnVariationalDiffusion):
     def sample(self, *args):
         raise NotImplementedError("Conditional model does not support sampling without given pocket.")
 
-    # ---- CUDA-graphed reverse loop ---------------------------------------------------
+    # ---- CUDA-graphed reverse loop ------------------------------------------------
     def _use_graph(self, device) -> bool:
         if self.loop_engine == 'eager':
             return False
@@ -120,73 +120,157 @@ class ConditionalDDPM(EnVariationalDiffusion):
 
     def _schedule_tables(self, steps, timesteps, device):
         """Per-step scalars for s = 0..steps-1 (t = s+1), computed with the same fp32 torch ops as the
-        eager step so both engines use bit-identical coefficients."""
+        eager step so both engines use bit-identical coefficients.  Columns of the second table:
+        reverse step (alpha_{t|s}, sigma^2_{t|s}/alpha_{t|s}/sigma_t, sigma_{t|s} sigma_s/sigma_t) |
+        inpainting (alpha_s, sigma_s, alpha_{t|s}, sigma_{t|s}) — conditional_model.py:162-183, :420-430."""
         s_int = torch.arange(steps, device=device).view(-1, 1)
         t_arr = (s_int + 1) / timesteps
         s_arr = s_int / timesteps
-        a, c, sg = self._step_coefficients(self.gamma(s_arr), self.gamma(t_arr), s_arr)
-        return t_arr.float().contiguous(), torch.cat([a, c, sg], dim=1).float().contiguous()
+        gamma_s, gamma_t = self.gamma(s_arr), self.gamma(t_arr)
+        a, c, sg = self._step_coefficients(gamma_s, gamma_t, s_arr)
+        _, sigma_ts, alpha_ts = self.sigma_and_alpha_t_given_s(gamma_t, gamma_s, s_arr)
+        inp = [self.alpha(gamma_s, s_arr), self.sigma(gamma_s, s_arr), alpha_ts, sigma_ts]
+        return t_arr.float().contiguous(), torch.cat([a, c, sg] + inp, dim=1).float().contiguous()
 
-    def _graphed_reverse_steps(self, z_lig, xh_pocket, lig_mask, pocket_mask, n_samples, first_s, n_steps, timesteps):
-        """Runs reverse steps s = first_s, first_s-1, ..., first_s-n_steps+1 by replaying one captured step."""
+    def _engine(self, z_lig, xh_pocket, lig_mask, pocket_mask, n_samples, timesteps):
+        """Static buffers + captured graphs for one batch layout.  A cached engine is reused only while everything a
+        captured graph bakes in is unchanged: batch layout (mask contents), the native module generation (packed-weight
+        blob), its arithmetic mode and its workspace/status buffers."""
         device = z_lig.device
         dyn: EGNNDynamics = self.dynamics
-        lib = _native.load()
+        dyn._ensure_handle(device)
         key = (tuple(z_lig.shape), tuple(xh_pocket.shape), n_samples, timesteps, str(device))
         st = self._graph_cache.get(key)
-        if st is not None and not (torch.equal(st['lig_mask'], lig_mask) and torch.equal(st['pocket_mask'], pocket_mask)):
-            st = None            # same shapes, different graph layout: re-capture
+        if st is not None:
+            same_layout = torch.equal(st['lig_mask'], lig_mask) and torch.equal(st['pocket_mask'], pocket_mask)
+            if not same_layout or st['sig'] != dyn.capture_signature():
+                st = None            # re-capture: a replay would use stale masks / freed weights / another kernel selection
         if st is None:
             self._graph_cache.clear()
             t_table, coef_table = self._schedule_tables(timesteps, timesteps, device)
-            # the captured step owns static copies of the masks, so one capture serves every later batch with the
+            # the captured steps own static copies of the masks, so one capture serves every later batch with the
             # same layout (generate_ligands builds fresh mask tensors on every call)
-            lig_mask, pocket_mask = lig_mask.clone(), pocket_mask.clone()
             st = dict(
                 z=torch.empty_like(z_lig), pocket=torch.empty_like(xh_pocket), noise=torch.empty_like(z_lig),
-                t=torch.zeros((n_samples, 1), device=device), coef=torch.zeros((n_samples, 3), device=device),
+                noise1=torch.empty_like(z_lig), noise2=torch.empty_like(z_lig),
+                t=torch.zeros((n_samples, 1), device=device), coef3=torch.zeros((n_samples, 3), device=device),
+                coef4=torch.zeros((n_samples, 4), device=device),
                 step=torch.zeros(1, dtype=torch.int64, device=device), t_table=t_table, coef_table=coef_table,
-                lig_mask=lig_mask, pocket_mask=pocket_mask, graph=None)
-
-            def one_step():
-                idx = st['step'].clamp(min=0)
-                st['t'].copy_(st['t_table'].index_select(0, idx).expand(n_samples, 1))
-                st['coef'].copy_(st['coef_table'].index_select(0, idx).expand(n_samples, 3))
-                eps, _ = dyn(st['z'], st['pocket'], st['t'], lig_mask, pocket_mask)
-                st['noise'].normal_()
-                _native.check(lib.dsb_ddpm_ligand_update(
-                    st['z'].data_ptr(), eps.data_ptr(), st['noise'].data_ptr(), st['coef'].data_ptr(),
-                    lig_mask.data_ptr(), pocket_mask.data_ptr(), st['pocket'].data_ptr(),
-                    z_lig.shape[0], xh_pocket.shape[0], n_samples, self.atom_nf, self.residue_nf,
-                    st['z'].data_ptr(), st['pocket'].data_ptr(),
-                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-                st['step'].sub_(1)
-
-            st['one_step'] = one_step
+                lig_mask=lig_mask.clone(), pocket_mask=pocket_mask.clone(), graphs={}, sig=None,
+                n_samples=n_samples, inpaint=None)
             self._graph_cache[key] = st
-        st['z'].copy_(z_lig)
-        st['pocket'].copy_(xh_pocket)
-        st['step'].fill_(first_s)
+        return st
+
+    def _captured_step(self, st, kind):
+        """One iteration as a python callable over the static buffers of ``st``.
+        kind: 'reverse' (z_t -> z_s, step -= 1) | 'inpaint_renoise' (reverse step + RePaint blend + re-noise to t) |
+        'inpaint_last' (reverse step + blend, step -= 1)."""
+        dyn: EGNNDynamics = self.dynamics
+        lib = _native.load()
+        lm, pm, n = st['lig_mask'], st['pocket_mask'], st['n_samples']
+        NL, NP = st['z'].shape[0], st['pocket'].shape[0]
+
+        def run():
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            idx = st['step'].clamp(min=0)
+            st['t'].copy_(st['t_table'].index_select(0, idx).expand(n, 1))
+            row = st['coef_table'].index_select(0, idx)
+            st['coef3'].copy_(row[:, :3].expand(n, 3))
+            st['coef4'].copy_(row[:, 3:].expand(n, 4))
+            eps, _ = dyn(st['z'], st['pocket'], st['t'], lm, pm)
+            st['noise'].normal_()
+            _native.check(lib.dsb_ddpm_ligand_update(
+                st['z'].data_ptr(), eps.data_ptr(), st['noise'].data_ptr(), st['coef3'].data_ptr(),
+                lm.data_ptr(), pm.data_ptr(), st['pocket'].data_ptr(), NL, NP, n, self.atom_nf, self.residue_nf,
+                st['z'].data_ptr(), st['pocket'].data_ptr(), stream))
+            if kind != 'reverse':
+                ip = st['inpaint']
+                st['noise1'].normal_()
+                renoise = kind == 'inpaint_renoise'
+                if renoise:
+                    st['noise2'].normal_()
+                _native.check(lib.dsb_ddpm_inpaint_update(
+                    st['z'].data_ptr(), st['pocket'].data_ptr(), ip['known'].data_ptr(), ip['com0'].data_ptr(),
+                    ip['fixed'].data_ptr(), st['noise1'].data_ptr(), st['noise2'].data_ptr() if renoise else None,
+                    st['coef4'].data_ptr(), lm.data_ptr(), pm.data_ptr(), NL, NP, n, self.atom_nf, self.residue_nf, stream))
+            if kind != 'inpaint_renoise':
+                st['step'].sub_(1)
+        return run
+
+    def _graph(self, st, kind, z_lig, xh_pocket, first_s):
+        """Captured CUDA graph of ``kind`` (captured on first use; capture leaves the static state as it found it)."""
+        g = st['graphs'].get(kind)
+        if g is not None:
+            return g
+        device = z_lig.device
+        dyn: EGNNDynamics = self.dynamics
+        run = self._captured_step(st, kind)
+
+        def reset():
+            st['z'].copy_(z_lig); st['pocket'].copy_(xh_pocket); st['step'].fill_(first_s)
+
+        # warm-up on a side stream (allocator + plan caches + workspace), restoring RNG and state afterwards
+        rng = torch.cuda.get_rng_state(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.set_rng_state(rng, device)
+        reset()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        reset()
+        st['graphs'][kind] = g
+        sig = dyn.capture_signature()
+        if st['sig'] is not None and st['sig'] != sig:      # e.g. the workspace grew during this warm-up: older captures are stale
+            st['graphs'] = {kind: g}
+        st['sig'] = sig
+        return g
+
+    def _graphed_reverse_steps(self, z_lig, xh_pocket, lig_mask, pocket_mask, n_samples, first_s, n_steps, timesteps):
+        """Runs reverse steps s = first_s, first_s-1, ..., first_s-n_steps+1 by replaying one captured step."""
+        dyn: EGNNDynamics = self.dynamics
+        st = self._engine(z_lig, xh_pocket, lig_mask, pocket_mask, n_samples, timesteps)
         prev_defer = dyn.defer_status_check
         dyn.defer_status_check = True
         try:
-            if st['graph'] is None:
-                # warm-up on a side stream (allocator + plan caches), restoring the state afterwards
-                rng = torch.cuda.get_rng_state(device)
-                side = torch.cuda.Stream(device=device)
-                side.wait_stream(torch.cuda.current_stream(device))
-                with torch.cuda.stream(side):
-                    st['one_step']()
-                torch.cuda.current_stream(device).wait_stream(side)
-                torch.cuda.set_rng_state(rng, device)
-                st['z'].copy_(z_lig); st['pocket'].copy_(xh_pocket); st['step'].fill_(first_s)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    st['one_step']()
-                st['graph'] = g
-                st['z'].copy_(z_lig); st['pocket'].copy_(xh_pocket); st['step'].fill_(first_s)
+            g = self._graph(st, 'reverse', z_lig, xh_pocket, first_s)
+            st['z'].copy_(z_lig); st['pocket'].copy_(xh_pocket); st['step'].fill_(first_s)
             for _ in range(n_steps):
-                st['graph'].replay()
+                g.replay()
+        finally:
+            dyn.defer_status_check = prev_defer
+        dyn.check_status()
+        return st['z'].clone(), st['pocket'].clone()
+
+    def _graphed_inpaint_loop(self, z_lig, xh_pocket, xh_known, com_pocket_0, lig_fixed, lmask, pmask, n_samples,
+                              timesteps, resamplings, return_frames, out_lig, out_pocket):
+        """The double loop of conditional_model.py:616-674 as graph replays: per (s, u) one captured graph = native
+        denoiser + fused reverse update + fused RePaint iteration (dsb_ddpm_inpaint_update); no torch op and no host
+        sync inside the loop."""
+        dyn: EGNNDynamics = self.dynamics
+        st = self._engine(z_lig, xh_pocket, lmask, pmask, n_samples, timesteps)
+        if st['inpaint'] is None:       # static buffers the captured RePaint iteration reads
+            st['inpaint'] = dict(known=torch.empty_like(z_lig), com0=torch.empty_like(com_pocket_0, dtype=torch.float32),
+                                 fixed=torch.empty(z_lig.shape[0], dtype=torch.float32, device=z_lig.device))
+        ip = st['inpaint']
+        ip['known'].copy_(xh_known); ip['com0'].copy_(com_pocket_0); ip['fixed'].copy_(lig_fixed.reshape(-1))
+        prev_defer = dyn.defer_status_check
+        dyn.defer_status_check = True
+        s0 = timesteps - 1
+        try:
+            g_last = self._graph(st, 'inpaint_last', z_lig, xh_pocket, s0)
+            g_re = self._graph(st, 'inpaint_renoise', z_lig, xh_pocket, s0) if resamplings > 1 else None
+            st['z'].copy_(z_lig); st['pocket'].copy_(xh_pocket); st['step'].fill_(s0)
+            for s in reversed(range(0, timesteps)):
+                for _ in range(resamplings - 1):
+                    g_re.replay()
+                g_last.replay()
+                if (s * return_frames) % timesteps == 0:
+                    idx = (s * return_frames) // timesteps
+                    out_lig[idx], out_pocket[idx] = self.unnormalize_z(st['z'], st['pocket'])
         finally:
             dyn.defer_status_check = prev_defer
         dyn.check_status()
@@ -280,37 +364,38 @@ class ConditionalDDPM(EnVariationalDiffusion):
         use_graph = self._use_graph(device)
         nd = self.n_dims
 
-        for s in reversed(range(0, timesteps)):
-            for u in range(resamplings):
-                s_array = torch.full((n_samples, 1), fill_value=s, device=device)
-                t_array = (s_array + 1) / timesteps
-                s_array = s_array / timesteps
-                gamma_t, gamma_s = self.gamma(t_array), self.gamma(s_array)
+        if use_graph:
+            z_lig, xh_pocket = self._graphed_inpaint_loop(z_lig, xh_pocket, xh_ligand, com_pocket_0, lig_fixed, lmask, pmask,
+                                                         n_samples, timesteps, resamplings, return_frames, out_lig, out_pocket)
+        else:
+            for s in reversed(range(0, timesteps)):
+                for u in range(resamplings):
+                    s_array = torch.full((n_samples, 1), fill_value=s, device=device)
+                    t_array = (s_array + 1) / timesteps
+                    s_array = s_array / timesteps
+                    gamma_t, gamma_s = self.gamma(t_array), self.gamma(s_array)
 
-                # denoise the whole ligand one step (unknown part)
-                if use_graph:
-                    z_unknown, xh_pocket = self._graphed_reverse_steps(z_lig, xh_pocket, lmask, pmask, n_samples, s, 1, timesteps)
-                else:
+                    # denoise the whole ligand one step (unknown part)
                     z_unknown, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, xh_pocket, lmask, pmask)
 
-                # noise the known part to level s, following the pocket's current COM (conditional_model.py:636-643)
-                com_pocket = scatter_mean(xh_pocket[:, :nd], pmask, dim=0)
-                xh_ligand[:, :nd] = ligand['x'] + (com_pocket - com_pocket_0)[lmask]
-                z_known, xh_pocket, _ = self.noised_representation(xh_ligand, xh_pocket, lmask, pmask, gamma_s)
+                    # noise the known part to level s, following the pocket's current COM (conditional_model.py:636-643)
+                    com_pocket = scatter_mean(xh_pocket[:, :nd], pmask, dim=0)
+                    xh_ligand[:, :nd] = ligand['x'] + (com_pocket - com_pocket_0)[lmask]
+                    z_known, xh_pocket, _ = self.noised_representation(xh_ligand, xh_pocket, lmask, pmask, gamma_s)
 
-                # align COM of the fixed atoms: noised -> denoised (conditional_model.py:645-656)
-                com_noised = scatter_mean(z_known[fixed_rows][:, :nd], lmask[fixed_rows], dim=0)
-                com_denoised = scatter_mean(z_unknown[fixed_rows][:, :nd], lmask[fixed_rows], dim=0)
-                dx = com_denoised - com_noised
-                z_known[:, :nd] = z_known[:, :nd] + dx[lmask]
-                xh_pocket[:, :nd] = xh_pocket[:, :nd] + dx[pmask]
+                    # align COM of the fixed atoms: noised -> denoised (conditional_model.py:645-656)
+                    com_noised = scatter_mean(z_known[fixed_rows][:, :nd], lmask[fixed_rows], dim=0)
+                    com_denoised = scatter_mean(z_unknown[fixed_rows][:, :nd], lmask[fixed_rows], dim=0)
+                    dx = com_denoised - com_noised
+                    z_known[:, :nd] = z_known[:, :nd] + dx[lmask]
+                    xh_pocket[:, :nd] = xh_pocket[:, :nd] + dx[pmask]
 
-                z_lig = z_known * lig_fixed + z_unknown * (1 - lig_fixed)
-                if u < resamplings - 1:
-                    z_lig, xh_pocket = self.sample_p_zt_given_zs(z_lig, xh_pocket, lmask, pmask, gamma_t, gamma_s)
-                if u == resamplings - 1 and (s * return_frames) % timesteps == 0:
-                    idx = (s * return_frames) // timesteps
-                    out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, xh_pocket)
+                    z_lig = z_known * lig_fixed + z_unknown * (1 - lig_fixed)
+                    if u < resamplings - 1:
+                        z_lig, xh_pocket = self.sample_p_zt_given_zs(z_lig, xh_pocket, lmask, pmask, gamma_t, gamma_s)
+                    if u == resamplings - 1 and (s * return_frames) % timesteps == 0:
+                        idx = (s * return_frames) // timesteps
+                        out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, xh_pocket)
 
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(z_lig, xh_pocket, lmask, pmask, n_samples)
         out_lig[0] = torch.cat([x_lig, h_lig], dim=1)

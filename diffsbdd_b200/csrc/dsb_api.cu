@@ -347,11 +347,12 @@ __device__ __forceinline__ int lb64(const int64_t* a, int n, int64_t v) {
   return lo;
 }
 
-__global__ void __launch_bounds__(128) ddpm_update_kernel(const float* __restrict__ z, const float* __restrict__ eps,
+// z/z_out and pocket/pocket_out may alias (in-place use is part of the contract): no __restrict__ on those pairs.
+__global__ void __launch_bounds__(128) ddpm_update_kernel(const float* z, const float* __restrict__ eps,
                                                            const float* __restrict__ noise, const float* __restrict__ coef,
                                                            const int64_t* __restrict__ mask_atoms, const int64_t* __restrict__ mask_res,
-                                                           const float* __restrict__ pocket, int NL, int NP, int A, int R,
-                                                           float* __restrict__ z_out, float* __restrict__ pocket_out) {
+                                                           const float* pocket, int NL, int NP, int A, int R,
+                                                           float* z_out, float* pocket_out) {
   const int g = blockIdx.x;
   const int l0 = lb64(mask_atoms, NL, g), l1 = lb64(mask_atoms, NL, (int64_t)g + 1);
   const int p0 = lb64(mask_res, NP, g), p1 = lb64(mask_res, NP, (int64_t)g + 1);
@@ -385,6 +386,103 @@ __global__ void __launch_bounds__(128) ddpm_update_kernel(const float* __restric
     const int c = idx % DR;
     const float v = pocket[idx];
     pocket_out[idx] = c < 3 ? v - com[c] : v;
+  }
+}
+
+
+// ---- fused RePaint iteration of ConditionalDDPM.inpaint (conditional_model.py:636-666) -------------------------------
+// sum of `nv` (<= 9) per-thread values over a 128-thread block; result valid in every thread.  `red` is [9][4] shared floats.
+__device__ __forceinline__ void block_sum(float* v, int nv, float (*red)[4]) {
+  for (int k = 0; k < nv; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __syncthreads();                      // previous use of `red` is complete
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < nv; ++k) red[k][threadIdx.x >> 5] = v[k];
+  __syncthreads();
+  for (int k = 0; k < nv; ++k) v[k] = (red[k][0] + red[k][1]) + (red[k][2] + red[k][3]);
+}
+
+// One block per graph.  On entry z = z_unknown (the reverse step's output), pocket = the pocket that step left.  In place:
+//   known part noised to level s around the pocket's current COM, ligand-COM removed (noised_representation, :162-183),
+//   COM of the fixed atoms aligned noised -> denoised (:645-656), blend (:659), optional re-noising step
+//   z_t ~ q(z_t | z_s) with its own COM removal (sample_p_zt_given_zs, :420-430, :662-666).
+// Every per-element fp32 operation is the one the torch ops of the eager loop perform, in the same order; only the
+// per-graph means are summed in a different order.
+__global__ void __launch_bounds__(128) ddpm_inpaint_kernel(float* z, float* pocket, const float* __restrict__ known,
+                                                            const float* __restrict__ com_pocket0, const float* __restrict__ fixed,
+                                                            const float* __restrict__ noise1, const float* __restrict__ noise2,
+                                                            const float* __restrict__ coef, const int64_t* __restrict__ mask_atoms,
+                                                            const int64_t* __restrict__ mask_res, int NL, int NP, int A, int R) {
+  const int g = blockIdx.x;
+  const int l0 = lb64(mask_atoms, NL, g), l1 = lb64(mask_atoms, NL, (int64_t)g + 1);
+  const int p0 = lb64(mask_res, NP, g), p1 = lb64(mask_res, NP, (int64_t)g + 1);
+  const int D = 3 + A, DR = 3 + R;
+  const float alpha_s = coef[g * 4 + 0], sigma_s = coef[g * 4 + 1], alpha_ts = coef[g * 4 + 2], sigma_ts = coef[g * 4 + 3];
+  __shared__ float red[9][4];
+  const float nl = (l1 - l0) > 0 ? (float)(l1 - l0) : 1.f, np_ = (p1 - p0) > 0 ? (float)(p1 - p0) : 1.f;
+
+  // pocket COM now vs. at the start: the known ligand follows the pocket (:636-640)
+  float v[9];
+  v[0] = v[1] = v[2] = 0.f;
+  for (int i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+    v[0] += pocket[(size_t)i * DR + 0]; v[1] += pocket[(size_t)i * DR + 1]; v[2] += pocket[(size_t)i * DR + 2];
+  }
+  block_sum(v, 3, red);
+  float shift[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) shift[c] = v[c] / np_ - com_pocket0[g * 3 + c];
+
+  auto zk_raw = [&](int idx, int c) {       // alpha_s * xh_known + sigma_s * eps   (:176)
+    const float xk = c < 3 ? known[idx] + shift[c] : known[idx];
+    return alpha_s * xk + sigma_s * noise1[idx];
+  };
+  // ligand COM of the noised known part (:180-182)
+  v[0] = v[1] = v[2] = 0.f;
+  for (int idx = l0 * D + threadIdx.x; idx < l1 * D; idx += blockDim.x) {
+    const int c = idx % D;
+    if (c < 3) v[c] += zk_raw(idx, c);
+  }
+  block_sum(v, 3, red);
+  float comk[3] = {v[0] / nl, v[1] / nl, v[2] / nl};
+  // COM of the fixed atoms: noised vs. denoised (:648-652)
+  for (int k = 0; k < 7; ++k) v[k] = 0.f;
+  for (int idx = l0 * D + threadIdx.x; idx < l1 * D; idx += blockDim.x) {
+    const int c = idx % D, i = idx / D;
+    if (c < 3 && fixed[i] != 0.f) { v[c] += zk_raw(idx, c) - comk[c]; v[3 + c] += z[idx]; if (c == 0) v[6] += 1.f; }
+  }
+  block_sum(v, 7, red);
+  const float nf = v[6] > 0.f ? v[6] : 1.f;
+  float dx[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dx[c] = v[3 + c] / nf - v[c] / nf;
+  // blend (+ re-noise)
+  float s2[3] = {0.f, 0.f, 0.f};
+  for (int idx = l0 * D + threadIdx.x; idx < l1 * D; idx += blockDim.x) {
+    const int c = idx % D, i = idx / D;
+    float zk = zk_raw(idx, c);
+    if (c < 3) zk = (zk - comk[c]) + dx[c];
+    const float f = fixed[i];
+    float o = zk * f + z[idx] * (1.f - f);                        // :659
+    if (noise2) { o = alpha_ts * o + sigma_ts * noise2[idx]; if (c < 3) s2[c] += o; }
+    z[idx] = o;
+  }
+  float com2[3] = {0.f, 0.f, 0.f};
+  if (noise2) {
+    block_sum(s2, 3, red);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) com2[c] = s2[c] / nl;
+    __syncthreads();
+    for (int i = l0 + threadIdx.x; i < l1; i += blockDim.x) {
+      z[(size_t)i * D + 0] -= com2[0]; z[(size_t)i * D + 1] -= com2[1]; z[(size_t)i * D + 2] -= com2[2];
+    }
+  }
+  for (int idx = p0 * DR + threadIdx.x; idx < p1 * DR; idx += blockDim.x) {
+    const int c = idx % DR;
+    if (c < 3) {
+      float q = (pocket[idx] - comk[c]) + dx[c];
+      if (noise2) q -= com2[c];
+      pocket[idx] = q;
+    }
   }
 }
 
@@ -663,6 +761,22 @@ int dsb_ddpm_ligand_update(const float* z_lig, const float* eps_hat, const float
   ddpm_update_kernel<<<(unsigned)n_graphs, 128, 0, (cudaStream_t)stream>>>(z_lig, eps_hat, noise, coef, mask_atoms, mask_residues,
                                                                           xh_pocket, (int)n_atoms, (int)n_residues, atom_nf,
                                                                           residue_nf, z_out, xh_pocket_out);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dsb_ddpm_inpaint_update(float* z_lig, float* xh_pocket, const float* xh_known, const float* com_pocket0,
+                            const float* lig_fixed, const float* noise_known, const float* noise_renoise, const float* coef,
+                            const int64_t* mask_atoms, const int64_t* mask_residues, int64_t n_atoms, int64_t n_residues,
+                            int64_t n_graphs, int32_t atom_nf, int32_t residue_nf, void* stream) {
+  if (n_graphs <= 0) return 0;
+  if (!z_lig || !xh_pocket || !xh_known || !com_pocket0 || !lig_fixed || !noise_known || !coef || !mask_atoms || !mask_residues) {
+    set_error("null pointer"); return DSB_ERR_INVALID_ARGUMENT;
+  }
+  ddpm_inpaint_kernel<<<(unsigned)n_graphs, 128, 0, (cudaStream_t)stream>>>(z_lig, xh_pocket, xh_known, com_pocket0, lig_fixed,
+                                                                           noise_known, noise_renoise, coef, mask_atoms,
+                                                                           mask_residues, (int)n_atoms, (int)n_residues, atom_nf,
+                                                                           residue_nf);
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }

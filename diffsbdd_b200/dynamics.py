@@ -144,6 +144,7 @@ class EGNNDynamics(nn.Module):
 
         self._handle: Optional[int] = None
         self._handle_sig = None
+        self._handle_gen = 0               # bumped on every (re)creation of the native module: CUDA-graph caches key on it
         self._plan = _PlanCache()
         self._workspace: Optional[torch.Tensor] = None
         self._status: Optional[torch.Tensor] = None
@@ -234,7 +235,17 @@ class EGNNDynamics(nn.Module):
             torch.cuda.current_stream().synchronize()
             _native.check(lib.dsb_dynamics_create(C.byref(ccfg), ptrs, len(names), C.byref(out)))
         self._handle, self._handle_sig = out.value, sig
+        self._handle_gen += 1
         _native.check(lib.dsb_dynamics_set_math_mode(C.c_void_p(self._handle), self.math_mode))
+
+    def capture_signature(self):
+        """Everything a captured CUDA graph of ``forward`` bakes in besides the batch layout: the native module (packed
+        weight blob), the kernel selection and the scratch/status buffers.  Samplers that replay captured graphs compare
+        this before every run and re-capture on a mismatch."""
+        ws = self._workspace.data_ptr() if self._workspace is not None else 0
+        stt = self._status.data_ptr() if self._status is not None else 0
+        pdl = int(_native.load().dsb_set_programmatic_launch(-1))
+        return (self._handle_gen, self._handle, self.math_mode, ws, stt, pdl)
 
     def _scratch(self, device, n_atoms, n_res, n_graphs, ecap) -> torch.Tensor:
         lib = _native.load()
@@ -257,14 +268,16 @@ class EGNNDynamics(nn.Module):
         if self._status is None:
             return
         flags = self._status.tolist()
-        if flags[0] or flags[2] or flags[3]:
+        if flags[0] or flags[2]:
             self._status.zero_()
         if flags[2]:
             raise RuntimeError('edge list overflowed edge_capacity (internal error)')
-        if flags[3]:
-            raise RuntimeError("an activation exceeded the fp16 range of math_mode='3xfp16'; set math_mode='3xtf32'")
         if flags[0]:
-            raise ValueError('NaN detected in EGNN output')
+            # dynamics.py:155-159.  In the 3xFP16 arithmetic an activation beyond the fp16 range (|x| > 65504) also ends
+            # here (inf -> NaN); the range-robust alternative is named in the message.
+            hint = " (if the inputs are finite: an activation may have left the fp16 range of math_mode='3xfp16' - " \
+                   "set math_mode='3xtf32')" if (self.math_mode & 8) else ''
+            raise ValueError('NaN detected in EGNN output' + hint)
 
     @property
     def last_num_edges(self) -> int:

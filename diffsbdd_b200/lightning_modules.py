@@ -79,9 +79,14 @@ class LigandPocketDDPM(_Base):
         self.dataset_info = _dataset_info(dataset)
         self.lig_type_encoder = dict(self.dataset_info['atom_encoder'])
         self.lig_type_decoder = list(self.dataset_info['atom_decoder'])
-        key = 'aa' if pocket_representation == 'CA' else 'atom'
-        self.pocket_type_encoder = dict(self.dataset_info[key + '_encoder'])
-        self.pocket_type_decoder = list(self.dataset_info[key + '_decoder'])
+        if pocket_representation == 'CA':
+            self.pocket_type_encoder = dict(self.dataset_info['aa_encoder'])
+            self.pocket_type_decoder = list(self.dataset_info['aa_decoder'])
+        else:
+            # full-atom pockets use the SAME vocabulary objects as the ligand (lightning_modules.py:90-97): with
+            # virtual_nodes the appended 'Ne' type therefore also widens aa_nf, as reference checkpoints expect
+            self.pocket_type_encoder = self.lig_type_encoder
+            self.pocket_type_decoder = self.lig_type_decoder
         self.virtual_nodes = virtual_nodes
         self.max_num_nodes = len(node_histogram) - 1
         symbol = 'Ne'

@@ -93,9 +93,9 @@ size_t dsb_dynamics_workspace_bytes(const dsb_dynamics* dyn, int64_t n_atoms, in
  *   status      device int32[4]: [0] |= 1 if a NaN reached the coordinate output (the reference raises
  *               ValueError("NaN detected in EGNN output"), dynamics.py:155-159 — the host wrapper
  *               turns the flag into that exception); [1] = number of edges of this call;
- *               [2] |= 1 if the edge list would not fit edge_capacity (outputs invalid); [3] |= 1 if an activation left
- *               the fp16 range in 3xFP16 mode (outputs invalid: rerun with 3xTF32).  Sticky: the library only ORs into
- *               [0], [2], [3]; the caller clears them.
+ *               [2] |= 1 if the edge list would not fit edge_capacity (outputs invalid); [3] reserved (always 0).
+ *               Sticky: the library only ORs into [0] and [2]; the caller clears them.  (3xFP16 mode: an activation
+ *               beyond the fp16 range becomes inf and reaches the output as NaN, i.e. flag [0].)
  * Inputs are not modified.  Asynchronous on `stream` (a cudaStream_t passed as void*). */
 int dsb_dynamics_forward(dsb_dynamics* dyn,
                          const float* xh_atoms, const float* xh_residues,
@@ -132,8 +132,8 @@ int dsb_set_programmatic_launch(int enable);
  * (x.w ~= x_lo.w_hi + x_hi.w_lo + x_hi.w_hi: fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance);
  * 8 selects the operand format of those kernels: 0 = 3xTF32 (kind::tf32, 8-bit exponent, any range),
  * 8 = 3xFP16 (kind::f16: half the shared-memory operand traffic, twice the MMA rate; weights are pre-scaled per matrix
- * and activations by 16 with exact powers of two; an activation with |16 x| > 60000 sets status[3] and the host
- * wrapper raises).  0 = fp32 FFMA kernels everywhere.  Only hidden_nf == 256 has tensor-core kernels. */
+ * with an exact power of two; an activation beyond the fp16 range turns into NaN at the output and raises through
+ * status[0]).  0 = fp32 FFMA kernels everywhere.  Only hidden_nf == 256 has tensor-core kernels. */
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode);
 
 /* ---- measurement hook (bench.py's live roofline).  When enabled, every non-captured forward brackets
@@ -160,6 +160,21 @@ int dsb_ddpm_ligand_update(const float* z_lig, const float* eps_hat, const float
                            const float* xh_pocket, int64_t n_atoms, int64_t n_residues,
                            int64_t n_graphs, int32_t atom_nf, int32_t residue_nf,
                            float* z_out, float* xh_pocket_out, void* stream);
+
+/* ---- fused RePaint iteration of ConditionalDDPM.inpaint (one launch; conditional_model.py:636-666), run right after
+ * dsb_ddpm_ligand_update, in place on its outputs (z_lig = z_unknown, xh_pocket):
+ *   xk      = xh_known, coordinates shifted by (COM(pocket) - com_pocket0[g])                         (:636-640)
+ *   z_known = alpha_s xk + sigma_s noise_known ; ligand COM of z_known removed from z_known and pocket   (:162-183)
+ *   dx      = COM_fixed(z_unknown) - COM_fixed(z_known) ; z_known.x += dx ; pocket.x += dx               (:645-656)
+ *   z       = z_known * fixed + z_unknown * (1 - fixed)                                                  (:659)
+ *   if noise_renoise != NULL:  z = alpha_ts z + sigma_ts noise_renoise, ligand COM removed from z and pocket  (:420-430, :662-666)
+ * xh_known [n_atoms, 3+atom_nf] (normalised known ligand), com_pocket0 [n_graphs, 3] (pocket COM before sampling),
+ * lig_fixed [n_atoms] (0/1 as fp32), coef [n_graphs, 4] = (alpha_s, sigma_s, alpha_{t|s}, sigma_{t|s}). */
+int dsb_ddpm_inpaint_update(float* z_lig, float* xh_pocket, const float* xh_known, const float* com_pocket0,
+                            const float* lig_fixed, const float* noise_known, const float* noise_renoise,
+                            const float* coef, const int64_t* mask_atoms, const int64_t* mask_residues,
+                            int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int32_t atom_nf,
+                            int32_t residue_nf, void* stream);
 
 const char* dsb_last_error(void);
 const char* dsb_version(void);

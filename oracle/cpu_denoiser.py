@@ -8,13 +8,15 @@ from . import egnn_oracle
 
 
 class OracleDynamics(nn.Module):
-    def __init__(self, cfg, state_dict):
+    def __init__(self, cfg, state_dict, device='cpu'):
         super().__init__()
-        self.cfg, self.sd = cfg, state_dict
+        self.cfg, self.device = cfg, device
+        self.sd = {k: v.to(device) for k, v in state_dict.items()}      # moved once, not per call
         self.update_pocket_coords = cfg.update_pocket_coords
         self.n_dims = cfg.n_dims
         self.calls = 0
 
     def forward(self, xh_atoms, xh_residues, t, mask_atoms, mask_residues):
         self.calls += 1
-        return egnn_oracle.denoiser_forward(self.cfg, self.sd, xh_atoms, xh_residues, t, mask_atoms, mask_residues)
+        return egnn_oracle.denoiser_forward(self.cfg, self.sd, xh_atoms, xh_residues, t, mask_atoms, mask_residues,
+                                            device=self.device)

@@ -38,7 +38,7 @@ def _mlp2(sd, prefix, x):
 def segment_sum(data, segment_ids, num_segments, normalization_factor, aggregation_method):
     """egnn_new.py:319-335 (``unsorted_segment_sum``): zero-init, scatter-add along dim 0, then
     '/normalization_factor' for 'sum' or '/count (0 -> 1)' for 'mean'."""
-    out = torch.zeros((num_segments, data.shape[1]), dtype=data.dtype)
+    out = torch.zeros((num_segments, data.shape[1]), dtype=data.dtype, device=data.device)
     idx = segment_ids.unsqueeze(-1).expand(-1, data.shape[1])
     out.scatter_add_(0, idx, data)
     if aggregation_method == 'sum':
@@ -147,19 +147,21 @@ def egnn_stack(sd, cfg, h, x, edges, update_coords_mask, batch_mask, edge_type_e
 
 def denoiser_forward(cfg, state_dict: Dict[str, torch.Tensor], xh_atoms, xh_residues, t,
                      mask_atoms, mask_residues, dtype=torch.float32,
-                     return_edges: bool = False):
+                     return_edges: bool = False, device='cpu'):
     """``EGNNDynamics.forward`` (dynamics.py:87-167), eval mode, ``mode='egnn_dynamics'``.
 
-    Returns ``(out_atoms [N_L,3+A], out_residues [N_P,3+R])`` on CPU in ``dtype``; raises
-    ``ValueError('NaN detected in EGNN output')`` like dynamics.py:155-159."""
+    Returns ``(out_atoms [N_L,3+A], out_residues [N_P,3+R])`` on ``device`` (default CPU: the checker) in ``dtype``;
+    raises ``ValueError('NaN detected in EGNN output')`` like dynamics.py:155-159.  ``device='cuda'`` runs the very same
+    ATen op sequence on the GPU: that is bench.py's ``--impl reference-gpu`` arm ("the reference's own PyTorch graph on
+    the B200"), never a checker and never the product path."""
     if cfg.mode != 'egnn_dynamics' or cfg.sin_embedding:
         raise NotImplementedError('oracle covers mode=egnn_dynamics, sin_embedding=False')
-    sd = {k: v.detach().to('cpu', dtype) for k, v in state_dict.items()}
-    xh_atoms = xh_atoms.detach().to('cpu', dtype)
-    xh_residues = xh_residues.detach().to('cpu', dtype)
-    t = t.detach().to('cpu', dtype)
-    mask_atoms = mask_atoms.detach().to('cpu', torch.int64)
-    mask_residues = mask_residues.detach().to('cpu', torch.int64)
+    sd = {k: v.detach().to(device, dtype) for k, v in state_dict.items()}
+    xh_atoms = xh_atoms.detach().to(device, dtype)
+    xh_residues = xh_residues.detach().to(device, dtype)
+    t = t.detach().to(device, dtype)
+    mask_atoms = mask_atoms.detach().to(device, torch.int64)
+    mask_residues = mask_residues.detach().to(device, torch.int64)
     nd = cfg.n_dims
     n_lig = len(mask_atoms)
 
@@ -179,7 +181,7 @@ def denoiser_forward(cfg, state_dict: Dict[str, torch.Tensor], xh_atoms, xh_resi
         assert torch.all(mask[edges[0]] == mask[edges[1]])       # dynamics.py:115
         emb = None
         if cfg.edge_embedding_dim:                                # dynamics.py:118-125
-            etype = torch.zeros(edges.shape[1], dtype=torch.int64)
+            etype = torch.zeros(edges.shape[1], dtype=torch.int64, device=edges.device)
             etype[(edges[0] < n_lig) & (edges[1] < n_lig)] = 1
             etype[(edges[0] >= n_lig) & (edges[1] >= n_lig)] = 2
             emb = sd['edge_embedding.weight'][etype]

@@ -50,6 +50,26 @@ def test_golden_forward_every_math_mode(case, mode):
     assert_close(got_r, want[1], f'{case} mode {mode} pocket out')
 
 
+H256_VARIANTS = ['joint_ca_h256_l6', 'reflect_h256_l3', 'sub2_h256_l2', 'noatt_notanh_h256_l2', 'emb8_h256_l3',
+                 'joint_emb8_sub2_reflect_h256_l2']
+
+
+@pytest.mark.parametrize('mode', ['fp32', '3xtf32', '3xfp16'])
+@pytest.mark.parametrize('case', H256_VARIANTS)
+def test_golden_h256_variants_every_arithmetic(case, mode):
+    """The branches the production config does not take, at hidden_nf=256 so that they run on the tcgen05 kernels too:
+    joint mode (all coordinate rows live, velocity mean removal; crossdock_ca_joint.yml dims), reflection-equivariant
+    (one coordinate MLP per tile), two sub-layers, no attention / no tanh, the edge-type table of the producers, and a
+    combination of them.  Goldens come from the unmodified reference (tests/golden/make_golden.py)."""
+    cfg, sd, inp, want, edges = load_golden(case)
+    net = make_net(cfg, sd)
+    net.math_mode = mode
+    got_a, got_r = run(net, inp)
+    assert net.last_num_edges == edges.shape[1]
+    assert_close(got_a, want[0], f'{case} mode {mode} ligand out')
+    assert_close(got_r, want[1], f'{case} mode {mode} pocket out')
+
+
 def test_tensor_core_mode_rejected_for_other_widths():
     cfg, sd, inp, want, _ = load_golden('joint_b2_h128_l5')
     net = make_net(cfg, sd)
@@ -234,3 +254,21 @@ def test_full_size_properties_config3():
     assert_close(one[1], out[1][sr], 'graph 5 alone vs batched (pocket)', atol=2e-6, rtol=1e-5)
     want = egnn_oracle.denoiser_forward(cfg, sd, *single)
     assert_close(one[0], want[0], 'graph 5 vs oracle')
+
+
+def test_full_batch_oracle_config3():
+    """BASELINE configs[2] at FULL size (B=64, N_L=25, N_P=175, 6 layers): every output row of the native kernels against
+    the CPU oracle (one oracle call, a few seconds on the box's host cores)."""
+    cfg = FULLATOM_COND
+    sd = syn.synthetic_state_dict(cfg, 0)
+    inp = syn.synthetic_denoiser_inputs(cfg, [25] * 64, [175] * 64, seed=3)
+    assert syn.min_cutoff_margin(cfg, inp[0], inp[1], inp[3], inp[4]) > 1e-5
+    torch.set_num_threads(min(32, torch.get_num_threads() or 1) or 1)
+    want = egnn_oracle.denoiser_forward(cfg, sd, *inp)
+    net = make_net(cfg, sd)
+    for mode in ('3xfp16', '3xtf32'):
+        net.math_mode = mode
+        got = run(net, inp)
+        ea = assert_close(got[0], want[0], f'full batch ligand out ({mode})')
+        er = assert_close(got[1], want[1], f'full batch pocket out ({mode})')
+        print(f'configs[2] full batch, {mode}: E={net.last_num_edges} max abs err ligand {ea:.2e} pocket {er:.2e}')

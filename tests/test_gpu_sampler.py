@@ -126,9 +126,9 @@ def test_graph_loop_matches_eager_loop_same_seed():
                      'the engines are then compared statistically in test_graph_loop_statistics')
     assert torch.equal(a[0][:, 3:], b[0][:, 3:])
     # second call with fresh mask tensors of the same layout must reuse the captured graph
-    g0 = next(iter(graph._graph_cache.values()))['graph']
+    g0 = next(iter(graph._graph_cache.values()))['graphs']['reverse']
     graph.sample_given_pocket(make_pocket('cuda'), n_lig.clone())
-    assert next(iter(graph._graph_cache.values()))['graph'] is g0
+    assert next(iter(graph._graph_cache.values()))['graphs']['reverse'] is g0
 
 
 def test_graph_loop_invariants_and_frames():
@@ -165,6 +165,138 @@ def test_graph_loop_statistics():
             xs.append(out[0][:, :3])
         spreads[engine] = float(torch.cat(xs).std())
     assert abs(spreads['eager'] - spreads['graph']) < 0.25 * spreads['eager']
+
+
+def test_fused_inpaint_kernel_matches_torch_ops():
+    """dsb_ddpm_inpaint_update against the torch ops of the eager RePaint iteration (conditional_model.py:636-666),
+    with and without the re-noising step, ragged graphs incl. a graph without fixed atoms."""
+    g = torch.Generator().manual_seed(1)
+    n_lig, n_poc = [6, 1, 9, 4], [11, 7, 3, 8]
+    A, R, B = 10, 10, 4
+    lm = torch.repeat_interleave(torch.arange(B), torch.tensor(n_lig)).cuda()
+    pm = torch.repeat_interleave(torch.arange(B), torch.tensor(n_poc)).cuda()
+    NL, NP = sum(n_lig), sum(n_poc)
+    z_unknown = torch.randn((NL, 3 + A), generator=g).cuda()
+    pocket = torch.randn((NP, 3 + R), generator=g).cuda()
+    known = torch.randn((NL, 3 + A), generator=g).cuda()
+    com0 = torch.randn((B, 3), generator=g).cuda()
+    fixed = (torch.rand(NL, generator=g) < 0.4).float().cuda()
+    fixed[lm == 3] = 0                       # a graph with nothing fixed
+    fixed[0] = 1
+    n1 = torch.randn((NL, 3 + A), generator=g).cuda()
+    n2 = torch.randn((NL, 3 + A), generator=g).cuda()
+    coef = (torch.rand((B, 4), generator=g) * 0.8 + 0.1).cuda()
+    lib = _native.load()
+    for renoise in (False, True):
+        # torch ops in eager order
+        com_pocket = scatter_mean(pocket[:, :3], pm)
+        xk = known.clone()
+        xk[:, :3] = known[:, :3] + (com_pocket - com0)[lm]
+        zk = coef[lm, 0:1] * xk + coef[lm, 1:2] * n1
+        pk = pocket.clone()
+        mean = scatter_mean(zk[:, :3], lm)
+        zk[:, :3] = zk[:, :3] - mean[lm]
+        pk[:, :3] = pk[:, :3] - mean[pm]
+        rows = fixed.bool()
+        cn = scatter_mean(zk[rows][:, :3], lm[rows], dim_size=B)
+        cd = scatter_mean(z_unknown[rows][:, :3], lm[rows], dim_size=B)
+        dx = cd - cn
+        zk[:, :3] = zk[:, :3] + dx[lm]
+        pk[:, :3] = pk[:, :3] + dx[pm]
+        want = zk * fixed[:, None] + z_unknown * (1 - fixed[:, None])
+        if renoise:
+            want = coef[lm, 2:3] * want + coef[lm, 3:4] * n2
+            m2 = scatter_mean(want[:, :3], lm)
+            want[:, :3] = want[:, :3] - m2[lm]
+            pk[:, :3] = pk[:, :3] - m2[pm]
+        z, p = z_unknown.clone(), pocket.clone()
+        _native.check(lib.dsb_ddpm_inpaint_update(
+            z.data_ptr(), p.data_ptr(), known.data_ptr(), com0.data_ptr(), fixed.data_ptr(), n1.data_ptr(),
+            n2.data_ptr() if renoise else None, coef.data_ptr(), lm.data_ptr(), pm.data_ptr(), NL, NP, B, A, R,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert torch.allclose(z, want, atol=3e-6, rtol=1e-5), float((z - want).abs().max())
+        assert torch.allclose(p, pk, atol=3e-6, rtol=1e-5), float((p - pk).abs().max())
+
+
+@pytest.mark.parametrize('resamplings,frames', [(1, 1), (3, 2)])
+def test_graph_inpaint_matches_eager_inpaint_same_seed(resamplings, frames):
+    """Default engine of ``inpaint`` on CUDA (captured denoiser + fused reverse update + fused RePaint iteration) against
+    the reference-order eager loop: same seed -> same randn stream (three draws per inner iteration, two on the last
+    resampling), so the trajectories agree to rounding."""
+    T = 6
+    eager = build(T, 'cuda', engine='eager')
+    graph = build(T, 'cuda', engine='auto')
+    outs = []
+    for ddpm in (eager, graph):
+        lig, fixed = make_ligand([8, 6], 3, device='cuda')
+        torch.manual_seed(5)
+        outs.append(ddpm.inpaint(lig, make_pocket('cuda'), fixed, resamplings=resamplings, return_frames=frames,
+                                 center='ligand'))
+    a, b = outs
+    st = next(iter(graph._graph_cache.values()))
+    assert 'inpaint_last' in st['graphs'] and (resamplings == 1 or 'inpaint_renoise' in st['graphs'])
+    assert a[0].shape == b[0].shape
+    scale = float(a[0][..., :3].abs().max())
+    assert torch.allclose(a[0][..., :3], b[0][..., :3], atol=1e-3 * scale), float((a[0] - b[0]).abs().max())
+    assert torch.allclose(a[1][..., :3], b[1][..., :3], atol=1e-3 * scale)
+    fa, fb = (a[0], b[0]) if frames == 1 else (a[0][0], b[0][0])
+    assert torch.equal(fa[:, 3:], fb[:, 3:])                      # argmax'd atom types of the final frame
+    # second call, fresh tensors, same layout: the captured graphs are reused
+    g0 = st['graphs']['inpaint_last']
+    lig, fixed = make_ligand([8, 6], 3, device='cuda')
+    graph.inpaint(lig, make_pocket('cuda'), fixed, resamplings=resamplings, return_frames=frames)
+    assert next(iter(graph._graph_cache.values()))['graphs']['inpaint_last'] is g0
+
+
+def test_graph_diversify_matches_eager_diversify_same_seed():
+    T = 10
+    outs = []
+    for engine in ('eager', 'auto'):
+        ddpm = build(T, 'cuda', engine=engine)
+        lig, _ = make_ligand([6, 6], 0, device='cuda')
+        torch.manual_seed(8)
+        outs.append(ddpm.diversify(lig, make_pocket('cuda'), noising_steps=4))
+    a, b = outs
+    scale = float(a[0][:, :3].abs().max())
+    assert torch.allclose(a[0][:, :3], b[0][:, :3], atol=1e-3 * scale), float((a[0] - b[0]).abs().max())
+    assert torch.equal(a[0][:, 3:], b[0][:, 3:])
+
+
+def test_captured_graph_is_dropped_when_weights_or_math_mode_change():
+    """a cached graph bakes in the packed-weight blob and the kernel selection.  After load_state_dict (or a
+    math_mode change) the same-shape call must re-capture, not replay freed weights."""
+    T = 5
+    n_lig = torch.tensor([7, 5]).cuda()
+    graph = build(T, 'cuda', engine='graph')
+    torch.manual_seed(21)
+    first = graph.sample_given_pocket(make_pocket('cuda'), n_lig)
+    g_old = next(iter(graph._graph_cache.values()))['graphs']['reverse']
+    sd2 = syn.synthetic_state_dict(DDPM_CFG, 99)
+    graph.dynamics.load_state_dict(sd2)
+    torch.manual_seed(21)
+    second = graph.sample_given_pocket(make_pocket('cuda'), n_lig)
+    assert next(iter(graph._graph_cache.values()))['graphs']['reverse'] is not g_old
+    eager = build(T, 'cuda', engine='eager')
+    eager.dynamics.load_state_dict(sd2)
+    torch.manual_seed(21)
+    want = eager.sample_given_pocket(make_pocket('cuda'), n_lig)
+    scale = float(want[0][:, :3].abs().max())
+    assert torch.allclose(second[0][:, :3], want[0][:, :3], atol=1e-3 * scale)
+    assert not torch.allclose(second[0][:, :3], first[0][:, :3], atol=1e-3 * scale)
+    # math-mode change on a hidden_nf=256 model: replay must not keep the old kernel selection
+    from diffsbdd_b200.config import CONFIG1
+    cfg = CONFIG1.with_(n_layers=2)
+    dyn = EGNNDynamics.from_config(cfg, device='cuda')
+    dyn.load_state_dict(syn.synthetic_state_dict(cfg, 3))
+    ddpm = ConditionalDDPM(dynamics=dyn, atom_nf=cfg.atom_nf, residue_nf=cfg.residue_nf, n_dims=3, timesteps=T,
+                           noise_schedule='polynomial_2', noise_precision=5e-4, loss_type='l2', norm_values=(1, 4),
+                           size_histogram=HIST).cuda().eval()
+    ddpm.sample_given_pocket(make_pocket('cuda'), n_lig)
+    g1 = next(iter(ddpm._graph_cache.values()))['graphs']['reverse']
+    dyn.math_mode = 'fp32'
+    ddpm.sample_given_pocket(make_pocket('cuda'), n_lig)
+    assert next(iter(ddpm._graph_cache.values()))['graphs']['reverse'] is not g1
 
 
 def _build_joint(T, device, native):
