@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 INSTR_LIB_PATH = os.path.join(HERE, 'libdiffsbdd_b200_instr.so')   # same sources with -DDSB_TC_INSTRUMENT=1 (profiles/tc_ablate.py)
 SOURCES = ['dsb_api.cu', 'dsb_node.cu', 'dsb_edge.cu', 'dsb_tc.cu']
 HEADERS = [os.path.join(CSRC, 'dsb_internal.cuh'), os.path.join(CSRC, 'dsb_tc.cuh'), os.path.join(HERE, '..', 'include', 'diffsbdd_b200.h')]
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++20',
               '-Xcompiler', '-fPIC', '-Wno-deprecated-gpu-targets']
 
 

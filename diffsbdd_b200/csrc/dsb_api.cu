@@ -146,9 +146,10 @@ struct Packer {
   // that puts max|w| into [4096, 8192) so that the low part of every non-tiny weight is a normal fp16.
   struct Blk { const float* src; int lds, scol, n_rows, n_dst_off; };
   unsigned* d_absmax = nullptr;
+  int tn = 256;                    // n-tile width of the images = hidden_nf
   void image(TcImage* img, int Nn, int K, const Blk* blk, int nblk) {
-    const size_t nt = (size_t)(Nn / 256) * (K / 32) * 8192;      // floats per TF32 image (hi or lo)
-    const size_t nh = (size_t)(Nn / 256) * (K / 64) * 8192;      // 32-bit words per FP16 image
+    const size_t nt = (size_t)Nn * K;            // floats per TF32 image (hi or lo): [Nn/tn][K/32][tn x 32]
+    const size_t nh = (size_t)Nn * K / 2;        // 32-bit words per FP16 image:       [Nn/tn][K/64][tn x 64 halfs]
     float* thi = alloc(nt); float* tlo = alloc(nt); float* hhi = alloc(nh); float* hlo = alloc(nh);
     img->t_hi = thi; img->t_lo = tlo; img->h_hi = hhi; img->h_lo = hlo; img->h_inv = 1.0f;
     if (dry) return;
@@ -162,8 +163,8 @@ struct Packer {
     if (amax > 0.f && amax < 3.0e38f) { int e; frexpf(amax, &e); scale = ldexpf(1.0f, 13 - e); }   // amax*scale in [4096, 8192)
     img->h_inv = 1.0f / scale;     // activation scale X_SCALE is 1
     for (int i = 0; i < nblk; ++i) {
-      launch_pack_b_image(thi, tlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K);
-      launch_pack_b_image_f16(hhi, hlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K, scale);
+      launch_pack_b_image(thi, tlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K, tn);
+      launch_pack_b_image_f16(hhi, hlo, blk[i].src, blk[i].lds, blk[i].scol, blk[i].n_rows, blk[i].n_dst_off, K, scale, tn);
     }
   }
   const float* copy(const float* src, int64_t n) {
@@ -183,6 +184,8 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
   auto P = [&](const std::string& n) -> const float* { return dry ? nullptr : params[index.at(n)]; };
   auto numel = [&](const std::string& n) { return tab[index.at(n)].numel; };
   Packer pk(dry ? nullptr : d->blob);
+  pk.tn = H;
+  const bool tc = tc_width_supported(H);
   PackedWeights& w = d->w;
   auto cp = [&](const std::string& n) { return pk.copy(P(n), numel(n)); };
 
@@ -239,7 +242,7 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
       { float* t = pk.alloc((size_t)H * H); G.W4 = pk.T(P(g + ".node_mlp.2.weight"), H, 0, H, H, t, H, 0); }
       G.b4 = cp(g + ".node_mlp.2.bias");
       G.iW1ab = G.iW2 = G.iW3 = G.iW4 = TcImage{nullptr, nullptr, nullptr, nullptr, 1.0f};
-      if (H == 256) {
+      if (tc) {
         const float* W1 = P(g + ".edge_mlp.0.weight");
         Packer::Blk b1[2] = {{W1, ld1, 0, H, 0}, {W1, ld1, H, H, H}};     // receiver part -> columns 0..H-1, sender -> H..2H-1
         pk.image(&G.iW1ab, 2 * H, H, b1, 2);
@@ -279,7 +282,7 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     Q.W1 = W1; Q.b1 = b1;
     Q.w3 = cp(q + ".coord_mlp.4.weight");
     Q.iW1 = Q.iW2[0] = Q.iW2[1] = TcImage{nullptr, nullptr, nullptr, nullptr, 1.0f};
-    if (H == 256) {
+    if (tc) {
       Packer::Blk blk[6];
       int nb = 0;
       for (int m = 0; m < nm; ++m) {
@@ -532,7 +535,7 @@ int dsb_dynamics_create(const dsb_config* cfg, const float* const* params, int n
   cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (int e = configure_node_kernels()) { cudaFree(d->blob); delete d; return e; }
   if (int e = configure_edge_kernels(cfg->hidden_nf)) { cudaFree(d->blob); delete d; return e; }
-  if (cfg->hidden_nf == 256) { if (int e = configure_tc_kernels()) { cudaFree(d->blob); delete d; return e; } }
+  if (tc_width_supported(cfg->hidden_nf)) { if (int e = configure_tc_kernels(cfg->hidden_nf)) { cudaFree(d->blob); delete d; return e; } }
   *out = d;
   return 0;
 }
@@ -635,7 +638,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     if (cls >= 0 && dyn->prof_n < kMaxProfEvents) { cudaEventRecord(dyn->prof_ev[2 * dyn->prof_n], s); cur_cls = cls; }
   };
 #define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
-  const int mm = (H == 256) ? dyn->math_mode : 0;
+  const int mm = tc_width_supported(H) ? dyn->math_mode : 0;
   const bool f16 = (mm & 8) != 0;
   auto gemm = [&](const GemmArgs& ga, const TcImage& img, int n_tile_off = 0) -> int {
     return ((mm & 1) && img.t_hi) ? launch_tc_node_gemm(dyn, ga, img, n_tile_off, f16, status, s) : launch_node_gemm(ga, s);
@@ -717,7 +720,7 @@ int dsb_set_programmatic_launch(int enable) {
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {
   if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
   if (mode < 0 || mode > 15) { set_error("math mode must be a bitmask in [0,15]"); return DSB_ERR_INVALID_ARGUMENT; }
-  if (mode != 0 && dyn->cfg.hidden_nf != 256) { set_error("the tcgen05 3xTF32 path is built for hidden_nf=256 only"); return DSB_ERR_UNSUPPORTED_CONFIG; }
+  if (mode != 0 && !tc_width_supported(dyn->cfg.hidden_nf)) { set_error("the tcgen05 kernels are built for hidden_nf 128, 192 and 256 only"); return DSB_ERR_UNSUPPORTED_CONFIG; }
   dyn->math_mode = mode;
   return 0;
 }

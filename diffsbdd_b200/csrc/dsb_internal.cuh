@@ -13,9 +13,9 @@ namespace dsb {
 constexpr int kMaxSub = 4;      // inv_sublayers supported per block
 constexpr int kMaxLayers = 16;
 
-// tensor-core operand images of one weight matrix B[n][k] (H == 256 only; all nullptr otherwise):
-//   t_*: TF32 hi/lo split, [Nn/256][K/32][256 rows x 128 B SWIZZLE_128B]
-//   h_*: FP16 hi/lo split of w * h_scale, [Nn/256][K/64][256 rows x 128 B]; h_inv = 1 / h_scale undoes the
+// tensor-core operand images of one weight matrix B[n][k] (hidden_nf H in {128,192,256}; all nullptr otherwise), n-tiles H wide:
+//   t_*: TF32 hi/lo split, [Nn/H][K/32][H rows x 128 B SWIZZLE_128B]
+//   h_*: FP16 hi/lo split of w * h_scale, [Nn/H][K/64][H rows x 128 B]; h_inv = 1 / h_scale undoes the
 //        weight scale and the activation scale in the epilogue (both powers of two: exact)
 struct TcImage {
   const float *t_hi, *t_lo;
@@ -113,7 +113,7 @@ struct dsb_dynamics {
   float* blob = nullptr;
   size_t blob_floats = 0;
   int num_sms = 148;
-  int math_mode = 0;         // bitmask: 1 node GEMMs, 2 edge_gcl, 4 edge_coord on tcgen05 (H == 256); 8: 3xFP16 split instead of 3xTF32
+  int math_mode = 0;         // bitmask: 1 node GEMMs, 2 edge_gcl, 4 edge_coord on tcgen05 (H in {128,192,256}); 8: 3xFP16 split instead of 3xTF32
   int last_launches = 0;     // kernels only
   int last_memsets = 0;
   // profiling
@@ -197,10 +197,11 @@ int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws
 int configure_edge_kernels(int H);
 
 // ---- tensor-core path (dsb_tc.cu) --------------------------------------------------------------------
-void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K);
-void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale);
+void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, int tn);
+void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale, int tn);
 void launch_absmax(const float* src, int lds, int scol, int n_rows, int K, unsigned* out);
-int configure_tc_kernels();
+int configure_tc_kernels(int H);
+bool tc_width_supported(int H);     // hidden_nf values with tensor-core kernels (128, 192, 256)
 int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, int n_tile_off, bool f16, int32_t* status,
                         cudaStream_t s);
 int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, bool f16, int32_t* status, cudaStream_t s);

@@ -19,50 +19,55 @@
 namespace dsb {
 using namespace tc;
 
-constexpr int H256 = 256;       // the tensor-core kernels are built for hidden_nf = 256
+
+// tuning switch (profiles/build_variants.py): 1 = producers of the node kernels issue their prefetch loads before the proxy fence
+#ifndef DSB_LOADS_BEFORE_FENCE
+#define DSB_LOADS_BEFORE_FENCE 0
+#endif
+constexpr bool kLoadsBeforeFence = DSB_LOADS_BEFORE_FENCE != 0;
 
 // =====================================================================================================
 // weight images: B[n][k] (= the reference's own [out][in] Linear layout) split into hi/lo and laid out as
-// [n_tile][k_chunk][256 rows x 128 B, SWIZZLE_128B] so that one k-chunk is a single 32 KB bulk copy.
+// [n_tile][k_chunk][H rows x 128 B, SWIZZLE_128B] (n-tiles are H = hidden_nf wide) so that one k-chunk is a single bulk copy.
 // =====================================================================================================
 __global__ void pack_b_image_kernel(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src, int lds,
-                                    int scol, int n_rows, int n_dst_off, int K, int chunks) {
+                                    int scol, int n_rows, int n_dst_off, int K, int chunks, int TN) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_rows * K) return;
   const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K);
   const int nd = n_dst_off + n, nt = nd / TN, nl = nd % TN;
   const int kc = k / TKC, c = (k % TKC) >> 2, j = k & 3;
-  const size_t off = ((size_t)nt * chunks + kc) * B_CHUNK_FLOATS + sw128_offset(nl, c) / 4 + j;
+  const size_t off = ((size_t)nt * chunks + kc) * (size_t)(TN * TKC) + sw128_offset(nl, c) / 4 + j;
   const float w = src[(size_t)n * lds + scol + k];
   const float h = tf32_hi(w);
   hi[off] = h;
   lo[off] = w - h;
 }
 
-void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K) {
+void launch_pack_b_image(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, int tn) {
   const int64_t tot = (int64_t)n_rows * K;
-  pack_b_image_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(hi, lo, src, lds, scol, n_rows, n_dst_off, K, K / TKC);
+  pack_b_image_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(hi, lo, src, lds, scol, n_rows, n_dst_off, K, K / TKC, tn);
 }
 
 // 3xFP16 images: w*scale = w_h + w_l in fp16, [n_tile][K/64][256 rows x 128 B (64 halfs), SWIZZLE_128B]
 __global__ void pack_b_image_f16_kernel(__half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ src, int lds,
-                                        int scol, int n_rows, int n_dst_off, int K, int chunks, float scale) {
+                                        int scol, int n_rows, int n_dst_off, int K, int chunks, float scale, int TN) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n_rows * K) return;
   const int n = (int)(idx / K), k = (int)(idx - (int64_t)n * K);
   const int nd = n_dst_off + n, nt = nd / TN, nl = nd % TN;
   const int kc = k / TKC16, c16 = (k % TKC16) >> 3, j = k & 7;
-  const size_t off = ((size_t)nt * chunks + kc) * (B_CHUNK_BYTES / 2) + sw128_offset(nl, c16) / 2 + j;
+  const size_t off = ((size_t)nt * chunks + kc) * (size_t)(TN * 64) + sw128_offset(nl, c16) / 2 + j;
   const float w = src[(size_t)n * lds + scol + k] * scale;
   const __half h = __float2half_rn(w);
   hi[off] = h;
   lo[off] = __float2half_rn(w - __half2float(h));
 }
 
-void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale) {
+void launch_pack_b_image_f16(float* hi, float* lo, const float* src, int lds, int scol, int n_rows, int n_dst_off, int K, float scale, int tn) {
   const int64_t tot = (int64_t)n_rows * K;
   pack_b_image_f16_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), src,
-                                                                  lds, scol, n_rows, n_dst_off, K, K / TKC16, scale);
+                                                                  lds, scol, n_rows, n_dst_off, K, K / TKC16, scale, tn);
 }
 
 // max |src[n][scol + k]| over an [n_rows][K] block -> *out (device uint holding the float bits; non-negative floats order as uints)
@@ -102,16 +107,17 @@ struct Carve {
   Control* ctl;
   char* extra;
 };
+template <int H>
 __device__ __forceinline__ Carve carve_smem(uint8_t* raw) {
   const uint32_t base = smem_u32(raw);
   const uint32_t pad = (1024u - (base & 1023u)) & 1023u;
   Carve c;
   c.stages = reinterpret_cast<char*>(raw) + pad;
-  c.ctl = reinterpret_cast<Control*>(c.stages + NSTAGE * STAGE_BYTES);
+  c.ctl = reinterpret_cast<Control*>(c.stages + NSTAGE * Geo<H>::STAGE_BYTES);
   c.extra = reinterpret_cast<char*>(c.ctl) + kControlBytes;
   return c;
 }
-constexpr size_t kTcSmemBase = 1024 + (size_t)NSTAGE * STAGE_BYTES + kControlBytes;
+template <int H> constexpr size_t tc_smem_base() { return 1024 + (size_t)NSTAGE * Geo<H>::STAGE_BYTES + kControlBytes; }
 constexpr int GEMM_T_STRIDE = 36;          // floats; 16-byte aligned rows, conflict-free for row-wise STS.128 and LDS.128
 
 __device__ __forceinline__ void tc_begin(Control* ctl, int warp, int scal_full_count = 1) {
@@ -128,15 +134,17 @@ __device__ __forceinline__ void tc_end(Control* ctl, int warp) {
   if (warp == MMA_WARP) tmem_dealloc(ctl->tmem_base, 512);
 }
 
+template <int H>
 __device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float* bhi, const float* blo, uint32_t& g, int chunks) {
+  using G = Geo<H>;
   for (int kc = 0; kc < chunks; ++kc, ++g) {
     const int s = g & 1;
     mbar_wait(&ctl->empty[s], ((g >> 1) & 1) ^ 1);
-    char* st = stages + (size_t)s * STAGE_BYTES + 2 * A_CHUNK_BYTES;
+    char* st = stages + (size_t)s * G::STAGE_BYTES + 2 * A_CHUNK_BYTES;
     if (tc_debug() & 1) { mbar_arrive(&ctl->full_w[s]); continue; }
-    mbar_arrive_expect_tx(&ctl->full_w[s], 2 * B_CHUNK_BYTES);
-    bulk_g2s(st, bhi + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
-    bulk_g2s(st + B_CHUNK_BYTES, blo + (size_t)kc * B_CHUNK_FLOATS, B_CHUNK_BYTES, &ctl->full_w[s]);
+    mbar_arrive_expect_tx(&ctl->full_w[s], 2 * G::B_CHUNK_BYTES);
+    bulk_g2s(st, bhi + (size_t)kc * G::B_CHUNK_FLOATS, G::B_CHUNK_BYTES, &ctl->full_w[s]);
+    bulk_g2s(st + G::B_CHUNK_BYTES, blo + (size_t)kc * G::B_CHUNK_FLOATS, G::B_CHUNK_BYTES, &ctl->full_w[s]);
   }
 }
 
@@ -158,7 +166,7 @@ struct TcGemmArgs {
 // live-tile enumeration: region A = m-tiles [0, dead_mt) x all n-tiles, region B = m-tiles [dead_mt, ntm) x n-tiles [dead_nt, ntn)
 struct TileMap {
   int ntn, ntm, dead_mt, dead_nt, nA, n_live;
-  __device__ TileMap(int M, int Nn, int dmt, int dnt) {
+  __device__ TileMap(int M, int Nn, int dmt, int dnt, int TN) {
     ntn = Nn / TN; ntm = (M + TM - 1) / TM;
     dead_nt = dnt; dead_mt = dnt > 0 ? (dmt < ntm ? dmt : ntm) : ntm;
     nA = dead_mt * ntn;
@@ -170,13 +178,15 @@ struct TileMap {
   }
 };
 
-template <bool F16>
+template <bool F16, int H>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs g) {
+  using G = Geo<H>;
+  constexpr int TN = H;
   extern __shared__ uint8_t smem_raw[];
-  const Carve cv = carve_smem(smem_raw);
+  const Carve cv = carve_smem<H>(smem_raw);
   Control* ctl = cv.ctl;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TileMap tm(g.M, g.Nn, g.dead_mt, g.dead_nt);
+  const TileMap tm(g.M, g.Nn, g.dead_mt, g.dead_nt, TN);
   const int n_tiles = tm.n_live;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   if (n_my == 0) return;
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       tc_fence_after();
       const long long e1 = gprof ? tc_clock() : 0;
       if (gprof && threadIdx.x == 0) atomicAdd(&g_tc_prof[17], (unsigned long long)(e1 - (it == 0 ? k1 : e0)));   // epilogue waits for the accumulator
-      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * TN);
+      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * ACC_STRIDE);
       // residual rows of column block cb+1 are requested while block cb is processed (two register sets, loop unrolled by 2)
       auto load_res = [&](int cb, float4 (&rr)[8]) {
         const int n = n0 + cb * 32 + tc4;
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     auto stage_chunk = [&](int q, float4 (&buf)[HPC][4]) {
       const int s = gc & 1;
       mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-      char* st = cv.stages + (size_t)s * STAGE_BYTES;
+      char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
       const int kc = q % chunks;
 #pragma unroll
       for (int h = 0; h < HPC; ++h) {
@@ -312,10 +322,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
           store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
         }
       }
-      if (q + 2 < total) load_chunk(q + 2, buf);
+      // fence.proxy.async waits for every outstanding load of the thread (FENCE.VIEW.ASYNC stalls on the long scoreboard,
+      // profiles/r1 source view): loads issued BEFORE it put a full L2 round trip between the stores and the arrive, on the
+      // MMA thread's critical path (wait-X 1.8 k cycles/chunk).  Issue the next loads after the hand-off instead.
+      if (kLoadsBeforeFence && q + 2 < total) load_chunk(q + 2, buf);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+      if (!kLoadsBeforeFence && q + 2 < total) load_chunk(q + 2, buf);
       ++gc;
     };
     float4 bufA[HPC][4], bufB[HPC][4];
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
     }
     if (gprof && ptid == 0) atomicAdd(&g_tc_prof[19], (unsigned long long)(tc_clock() - p0));    // producers: all tiles of this CTA
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks, 0);
+    if (lane == 0) mma_role<F16, H>(ctl, cv.stages, n_my, chunks, 0);
     __syncwarp();
   } else {
     if (lane == 0) {
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       for (int it = 0; it < n_my; ++it) {
         int mt_, nt;
         tm.get(blockIdx.x + it * gridDim.x, mt_, nt);
-        tma_role(ctl, cv.stages, g.Bhi + (size_t)nt * chunks * B_CHUNK_FLOATS, g.Blo + (size_t)nt * chunks * B_CHUNK_FLOATS, gc, chunks);
+        tma_role<H>(ctl, cv.stages, g.Bhi + (size_t)nt * chunks * G::B_CHUNK_FLOATS, g.Blo + (size_t)nt * chunks * G::B_CHUNK_FLOATS, gc, chunks);
       }
     }
     __syncwarp();
@@ -369,10 +383,12 @@ struct TcMlpArgs {
   int32_t* status;
 };
 
-template <bool F16>
+template <bool F16, int H>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g) {
+  using G = Geo<H>;
+  constexpr int TN = H;
   extern __shared__ uint8_t smem_raw[];
-  const Carve cv = carve_smem(smem_raw);
+  const Carve cv = carve_smem<H>(smem_raw);
   Control* ctl = cv.ctl;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntm = (g.M + TM - 1) / TM;
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
   if (n_my == 0) return;
   constexpr int KPC = F16 ? TKC16 : TKC;        // k-values per pipeline chunk
   constexpr int CB_PER_CHUNK = KPC / 32;        // 32-column accumulator blocks per phase-2 chunk
-  constexpr int C1 = 2 * H256 / KPC, C2 = H256 / KPC, CT = C1 + C2;
+  constexpr int C1 = 2 * H / KPC, C2 = H / KPC, CT = C1 + C2;
   constexpr int HPC = F16 ? 2 : 1;
   pdl_trigger();
   tc_begin(ctl, warp);
@@ -402,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
         const uint32_t q = q0 + cb / CB_PER_CHUNK;
         const int s = q & 1;
         if (cb % CB_PER_CHUNK == 0) mbar_wait(&ctl->empty[s], ((q >> 1) & 1) ^ 1);
-        char* st = cv.stages + (size_t)s * STAGE_BYTES;
+        char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
         float v[32];
         tmem_ld32(tbase + cb * 32, v);
         const f32x2 ip = pk2(g.inv3, g.inv3);
@@ -429,7 +445,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
       // ---- phase-2 epilogue: h <- h + acc * inv4 + b4, aggregate re-armed
       mbar_wait(&ctl->acc_full[1], it & 1);
       tc_fence_after();
-      const uint32_t taddr = tbase + (uint32_t)TN;
+      const uint32_t taddr = tbase + (uint32_t)ACC_STRIDE;
       auto load_res = [&](int cb, float4 (&rr)[8]) {
         const int n = cb * 32 + tc4;
 #pragma unroll
@@ -494,8 +510,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
         for (int i = 0; i < 4; ++i) {
           const int m = m0 + 16 * pw + 4 * sr + i;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < g.M) x = k < H256 ? *reinterpret_cast<const float4*>(g.h + (size_t)m * g.ldh + k)
-                                    : *reinterpret_cast<const float4*>(g.agg + (size_t)m * g.ldagg + (k - H256));
+          if (m < g.M) x = k < H ? *reinterpret_cast<const float4*>(g.h + (size_t)m * g.ldh + k)
+                                    : *reinterpret_cast<const float4*>(g.agg + (size_t)m * g.ldagg + (k - H));
           buf[h][i] = x;
         }
       }
@@ -505,10 +521,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
       const uint32_t q = (uint32_t)it * CT + kc;
       const int s = q & 1;
       mbar_wait(&ctl->empty[s], ((q >> 1) & 1) ^ 1);
-      char* st = cv.stages + (size_t)s * STAGE_BYTES;
+      char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
 #pragma unroll
       for (int h = 0; h < HPC; ++h) {
-        const bool second = (kc * HPC + h) * TKC + 4 * pc >= H256;       // aggregate columns: exact division by the normalisation
+        const bool second = (kc * HPC + h) * TKC + 4 * pc >= H;       // aggregate columns: exact division by the normalisation
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 x = buf[h][i];
@@ -516,10 +532,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
           store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
         }
       }
-      if (j + 2 < total) load_chunk(j + 2, buf);
+      if (kLoadsBeforeFence && j + 2 < total) load_chunk(j + 2, buf);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+      if (!kLoadsBeforeFence && j + 2 < total) load_chunk(j + 2, buf);      // see tc_node_gemm_kernel
     };
     float4 bufA[HPC][4], bufB[HPC][4];
     load_chunk(0, bufA);
@@ -536,7 +553,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
         for (int ph = 0; ph < 2; ++ph) {
           mbar_wait(&ctl->epi_done[ph], (it & 1) ^ 1);        // accumulator ph drained by the epilogue of the previous tile
           tc_fence_after();
-          const uint32_t d = ctl->tmem_base + (uint32_t)(ph * TN);
+          const uint32_t d = ctl->tmem_base + (uint32_t)(ph * ACC_STRIDE);
           const int nchunks = ph == 0 ? C1 : C2;
           for (int kc = 0; kc < nchunks; ++kc, ++q) {
             const int s = q & 1;
@@ -544,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
             mbar_wait(&ctl->full_w[s], par);
             mbar_wait(&ctl->full_x[s], par);
             tc_fence_after();
-            mma_issue_chunk<F16>(d, cv.stages + (size_t)s * STAGE_BYTES, kc == 0);
+            mma_issue_chunk<F16, H>(d, cv.stages + (size_t)s * G::STAGE_BYTES, kc == 0);
             umma_commit(&ctl->empty[s]);
           }
           umma_commit(&ctl->acc_full[ph]);
@@ -556,8 +573,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
     if (lane == 0) {
       uint32_t gc = 0;
       for (int it = 0; it < n_my; ++it) {
-        tma_role(ctl, cv.stages, g.W3hi, g.W3lo, gc, C1);
-        tma_role(ctl, cv.stages, g.W4hi, g.W4lo, gc, C2);
+        tma_role<H>(ctl, cv.stages, g.W3hi, g.W3lo, gc, C1);
+        tma_role<H>(ctl, cv.stages, g.W4hi, g.W4lo, gc, C2);
       }
     }
     __syncwarp();
@@ -568,30 +585,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
 // =====================================================================================================
 // edge kernels
 // =====================================================================================================
-// unroll factors of the three hot loops (overridable for tuning builds: -DDSB_P_UNROLL=... etc.)
-#ifndef DSB_P_UNROLL
-#define DSB_P_UNROLL 1
-#endif
+// unroll factors of the epilogue loops (overridable for tuning builds: -DDSB_E1_UNROLL=... etc.)
 #ifndef DSB_E1_UNROLL
 #define DSB_E1_UNROLL 1
 #endif
 #ifndef DSB_E2_UNROLL
 #define DSB_E2_UNROLL 1
 #endif
-constexpr int kPUnroll = DSB_P_UNROLL, kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
+constexpr int kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
 constexpr int EPI_T_STRIDE = 36;          // 16-byte aligned rows: conflict-free row-wise STS.128 and column-wise LDS.32
-constexpr int NSCAL = 3;                   // scalar buffer sets (tile it uses set it % NSCAL)
+constexpr int NSCAL = 3;                   // scalar buffer sets (the j-th tile of a CTA uses set j % NSCAL)
 constexpr int SCAL_WARPS = 2;              // warps 14, 15 of the edge kernels: per-edge scalars one tile ahead of the producers
 constexpr int EDGE_THREADS = TC_THREADS + SCAL_WARPS * 32;   // 512
 
+template <int H>
 struct EdgeExtra {            // shared memory after Control
-  float vec[2][3 * H256];     // per MLP: wr, wr0, b2   (the edge-type table tb stays in global/L1)
-  float wa[H256];             // attention weight (GCL) or w3 (coord)
+  float vec[2][3 * H];     // per MLP: wr, wr0, b2   (the edge-type table tb stays in global/L1)
+  float wa[H];                // attention weight (GCL) or w3 (coord)
   float d2[NSCAL][TM], d0[NSCAL][TM];       // per-edge scalars: NSCAL sets so the scalar warps run a full tile ahead of the
   int row[NSCAL][TM], col[NSCAL][TM], type[NSCAL][TM];   // producers while the epilogue still reads the set of the tile before
   union {
     float T[EPI_WARPS][32 * EPI_T_STRIDE];                     // GCL: per-warp transpose buffer
-    struct { float dir[NSCAL][6][TM]; float T4[EPI_WARPS][32 * 4]; } c;   // coord: directions + small transpose buffer
+    struct { float dir[NSCAL][3][TM]; float T4[EPI_WARPS][32 * 4]; } c;   // coord: direction of this MLP + small transpose buffer
   } u;
 };
 
@@ -600,7 +615,7 @@ struct TcEdgeArgs {
   const float4* x; const float4* cent; const int32_t* gid;
   const int32_t* vrow_ptr; const int32_t* vmap; int n_rows;   // virtual rows [0, vrow_ptr[n_rows]): vmap[v] = edge index or -1 (pad)
   const int32_t *erow, *ecol; const float* ed0; int NL;
-  int nm;                                    // MLPs per tile: 1 (GCL, reflection-equivariant coord) or 2 (coord + cross)
+  int nm;                                    // MLPs per edge tile: 1 (GCL, reflection-equivariant coord) or 2 (coord + cross)
   const float* W2hi[2]; const float* W2lo[2];   // [8][8192] images
   const float* wr[2]; const float* wr0[2]; const float* tb[2]; const float* b2[2];
   const float* wa; const float* ba;          // GCL attention (nullptr: none) / coord: wa = w3
@@ -611,13 +626,13 @@ struct TcEdgeArgs {
   int32_t* status;
 };
 
-// per-edge scalars of tile `e0` (thread pr handles edge e0 + pr), written by the scalar warps
-template <bool COORD>
-__device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex, int par, int pr, int v0, int V) {
+// per-edge scalars of edge tile v0/TM for MLP m (thread pr handles virtual row v0 + pr), written by the scalar warps
+template <bool COORD, int H>
+__device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra<H>* ex, int par, int pr, int v0, int V, int m) {
   const int vr = v0 + pr;
   const int e = vr < V ? a.vmap[vr] : -1;
   int r = -1, c = 0, ty = 0; float d2 = 0.f, d0 = 0.f;
-  float dir[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dir[3] = {0.f, 0.f, 0.f};
   if (e >= 0) {
     r = a.erow[e]; c = a.ecol[e]; d0 = a.ed0[e];
     const float4 xi = a.x[r], xj = a.x[c];
@@ -625,91 +640,96 @@ __device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra* ex,
     d2 = dx * dx + dy * dy + dz * dz;
     ty = (r < a.NL) == (c < a.NL) ? (r < a.NL ? 1 : 2) : 0;
     if (COORD) {
-      const float den = sqrtf(d2 + 1e-8f) + a.norm_constant;            // egnn_new.py:300-301
-      dir[0] = dx / den; dir[1] = dy / den; dir[2] = dz / den;
-      if (a.nm == 2) {                                                   // egnn_new.py:312-315
-        const float4 m = a.cent[a.gid[r]];
-        const float ax = xi.x - m.x, ay = xi.y - m.y, az = xi.z - m.z;
-        const float bx = xj.x - m.x, by = xj.y - m.y, bz = xj.z - m.z;
+      if (m == 0) {                                                     // egnn_new.py:300-301 (coord2diff)
+        const float den = sqrtf(d2 + 1e-8f) + a.norm_constant;
+        dir[0] = dx / den; dir[1] = dy / den; dir[2] = dz / den;
+      } else {                                                          // egnn_new.py:312-315 (coord2cross)
+        const float4 mu = a.cent[a.gid[r]];
+        const float ax = xi.x - mu.x, ay = xi.y - mu.y, az = xi.z - mu.z;
+        const float bx = xj.x - mu.x, by = xj.y - mu.y, bz = xj.z - mu.z;
         const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
         const float cn = sqrtf(cx * cx + cy * cy + cz * cz) + a.norm_constant;
-        dir[3] = cx / cn; dir[4] = cy / cn; dir[5] = cz / cn;
+        dir[0] = cx / cn; dir[1] = cy / cn; dir[2] = cz / cn;
       }
     }
   }
   ex->row[par][pr] = r; ex->col[par][pr] = c; ex->d2[par][pr] = d2; ex->d0[par][pr] = d0; ex->type[par][pr] = ty;
   if (COORD) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) ex->u.c.dir[par][k][pr] = dir[k];
+    for (int k = 0; k < 3; ++k) ex->u.c.dir[par][k][pr] = dir[k];
   }
 }
 
-// Virtual tile vt = tile * nm + m  (m-th MLP of the tile).  par(tile) selects the scalar buffers, a = vt & 1 the accumulator.
-template <bool COORD, bool F16>
+// Work unit = virtual tile v = edge_tile * nm + m (the m-th MLP over 128 virtual edge rows).  The coordinate update is a sum
+// of independent terms per MLP (egnn_new.py:100-109: trans = diff * f(phi) + cross * f(phi_x)), so the two MLPs of an edge tile
+// are independent units that add into the same receiver sums: units, not edge tiles, are dealt round-robin to the CTAs (610 edge
+// tiles on 148 CTAs would leave 21 % of the machine idle in the last wave; 1220 units leave 9 %).  The j-th unit of a CTA uses
+// scalar set j % NSCAL and accumulator j & 1.
+template <bool COORD, bool F16, int H>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
+  using G = Geo<H>;
+  constexpr int TN = H;
   extern __shared__ uint8_t smem_raw[];
-  const Carve cv = carve_smem(smem_raw);
+  const Carve cv = carve_smem<H>(smem_raw);
   Control* ctl = cv.ctl;
-  EdgeExtra* ex = reinterpret_cast<EdgeExtra*>(cv.extra);
+  EdgeExtra<H>* ex = reinterpret_cast<EdgeExtra<H>*>(cv.extra);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nm = a.nm;
-  constexpr int halves = H256 / TKC;           // 32-k production steps per virtual tile
-  constexpr int chunks = F16 ? halves / 2 : halves;
+  constexpr int halves = H / TKC;           // 32-k production steps per unit
+  constexpr int HPC = F16 ? 2 : 1;             // production steps per pipeline chunk (stage)
+  constexpr int chunks = halves / HPC;
   const bool has_tb = a.tb[0] != nullptr;
 
   pdl_trigger();
-  for (int i = threadIdx.x; i < H256; i += EDGE_THREADS) {
+  for (int i = threadIdx.x; i < H; i += EDGE_THREADS) {
     for (int m = 0; m < nm; ++m) {
       float* v = ex->vec[m];
-      v[i] = a.wr[m][i]; v[H256 + i] = a.wr0[m][i]; v[2 * H256 + i] = a.b2[m][i];
+      v[i] = a.wr[m][i]; v[H + i] = a.wr0[m][i]; v[2 * H + i] = a.b2[m][i];
     }
     ex->wa[i] = a.wa ? a.wa[i] : 0.f;
   }
   tc_begin(ctl, warp, SCAL_WARPS);        // contains the __syncthreads that publishes the vectors
   pdl_wait();                 // everything above touches only kernel arguments and constant weights
   const int E = a.vrow_ptr[a.n_rows];          // virtual rows: every receiver's edges start at a multiple of kRowChunk
-  const int n_tiles = (E + TM - 1) / TM;
-  const int n_my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (n_my_tiles == 0) { tc_end(ctl, warp); return; }
-  const int n_my = n_my_tiles * nm;            // virtual tiles
+  const int n_units = ((E + TM - 1) / TM) * nm;
+  const int n_my = ((int)blockIdx.x < n_units) ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (n_my == 0) { tc_end(ctl, warp); return; }
+  auto unit_tile = [&](int j, int& m) { const int v = blockIdx.x + j * gridDim.x; const int t = v / nm; m = v - t * nm; return t; };
 
   if (warp < EPI_WARPS) {
     // ------------------------------------------------------------------------------------------ epilogue
     const bool has_att = (!COORD) && a.wa != nullptr;
     const float ba = has_att ? a.ba[0] : 0.f;
     float* T = COORD ? ex->u.c.T4[warp] : ex->u.T[warp];
-    float phi0 = 0.f;
     const long long ep0 = (!COORD && (tc_debug() & 512) && warp == 0 && lane == 0) ? tc_clock() : 0;
-    for (int vt = 0; vt < n_my; ++vt) {
-      const int it = vt / nm, m = vt - it * nm;
-      const int par = it % NSCAL, acc = vt & 1;
-      const uint32_t sph = (uint32_t)(it / NSCAL) & 1u;          // phase of this use of scalar set `par`
+    for (int j = 0; j < n_my; ++j) {
+      int m;
+      unit_tile(j, m);
+      const int par = j % NSCAL, acc = j & 1;
+      const uint32_t sph = (uint32_t)(j / NSCAL) & 1u;          // phase of this use of scalar set `par`
       const bool prof_on = !COORD && (tc_debug() & 512) && warp == 0 && lane == 0;     // cycle accounting: GCL kernel only
       long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       if (prof_on) c0 = tc_clock();
-      if (m == 0) mbar_wait(&ctl->scal_full[par], sph);
-      mbar_wait(&ctl->acc_full[acc], (vt >> 1) & 1);
+      mbar_wait(&ctl->scal_full[par], sph);
+      mbar_wait(&ctl->acc_full[acc], (j >> 1) & 1);
       tc_fence_after();
       if (prof_on) c1 = tc_clock();
-      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * TN);
-      const float* b2 = ex->vec[m] + 2 * H256;
+      const uint32_t taddr = ctl->tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_STRIDE);
+      const float* b2 = ex->vec[m] + 2 * H;
       const float inv = a.inv_scale[m];
       const int myrow = ex->row[par][warp * 32 + lane];
       if (tc_debug() & 4) {
         tc_fence_before(); __syncwarp();
-        if (lane == 0) { mbar_arrive(&ctl->epi_done[acc]); if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]); }
+        if (lane == 0) { mbar_arrive(&ctl->epi_done[acc]); mbar_arrive(&ctl->scal_empty[par]); }
         continue;
       }
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
       f32x2 s01 = pk2(0.f, 0.f), s23 = s01;      // four independent partial dot products
       const int edbg = tc_debug();
-      long long ld_cyc = 0;
 #pragma unroll kE1Unroll
       for (int cb = 0; cb < TN / 32; ++cb) {
         float v[32];
-        const long long l0 = prof_on ? tc_clock() : 0;
         tmem_ld32(taddr + cb * 32, v);
-        if (prof_on) ld_cyc += tc_clock() - l0;
         if (!(edbg & 32))
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -733,10 +753,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       float s0, s1, s2, s3;
       upk2(s01, s0, s1); upk2(s23, s2, s3);
       const float s = (s0 + s1) + (s2 + s3);
-      if (prof_on) { c2 = tc_clock(); atomicAdd(&g_tc_prof[4], (unsigned long long)ld_cyc); }
+      if (prof_on) c2 = tc_clock();
       if (!COORD) {
         tmem_wait_st();
-        if (prof_on) atomicAdd(&g_tc_prof[28], (unsigned long long)(tc_clock() - c2));     // tcgen05.wait::st after pass 1
         const float gate = myrow >= 0 ? (has_att ? sigmoid_f(s + ba) : 1.0f) : 0.f;    // pad rows share a chunk with real rows: weight 0
         // Receiver segments start at multiples of kRowChunk rows (virtual edge order), so every chunk of 4 rows belongs to one
         // receiver (or is padding): no segment search.  crow[k] = receiver of chunk k of this warp's 32 rows.
@@ -751,9 +770,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
 #pragma unroll kE2Unroll
         for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
-          const long long l0 = prof_on ? tc_clock() : 0;
           tmem_ld32(taddr + cb * 32, v);
-          const long long l1 = prof_on ? tc_clock() : 0;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
           {
@@ -763,8 +780,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
             *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) = o;
           }
           __syncwarp();
-          if (prof_on) { atomicAdd(&g_tc_prof[5], (unsigned long long)(l1 - l0)); atomicAdd(&g_tc_prof[6], (unsigned long long)(tc_clock() - l1)); }
-          const long long g0 = prof_on ? tc_clock() : 0;
           if (!(edbg & 1024)) {
             const float* tp = T + lane;
             float* dst = a.agg + cb * 32 + lane;
@@ -774,175 +789,168 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const float sum = (t[4 * k] + t[4 * k + 1]) + (t[4 * k + 2] + t[4 * k + 3]);
-              atomicAdd(dst + (size_t)crow[k] * H256, sum);
+              atomicAdd(dst + (size_t)crow[k] * H, sum);
             }
           }
           __syncwarp();
-          if (prof_on) atomicAdd(&g_tc_prof[29], (unsigned long long)(tc_clock() - g0));   // chunk sums + REDs of one column block
         }
       } else {
-        // coord: s = phi_m for this edge row
+        // coord: s = phi_m for this edge row; this unit's term of trans (egnn_new.py:100-109)
         const int r = warp * 32 + lane;
-        if (m == 0 && nm == 2) {
-          phi0 = s;                 // the same thread owns this edge row for both MLPs of the tile
-        } else {
-          const float p0 = (nm == 2) ? phi0 : s;
-          const float p1 = s;
-          float tr[3];
+        float tr[3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {     // egnn_new.py:100-109
-            float t = a.use_tanh ? (ex->u.c.dir[par][k][r] * tanhf(p0)) * a.coords_range : ex->u.c.dir[par][k][r] * p0;
-            if (nm == 2) {
-              const float pc = a.use_tanh ? tanhf(p1) * a.coords_range : p1;
-              t = t + ex->u.c.dir[par][3 + k][r] * pc;
-            }
-            tr[k] = myrow >= 0 ? t : 0.f;
-          }
-          // 4-row chunks belong to one receiver: lane = (chunk k, component) sums 4 rows and issues one RED
-          T[lane * 4 + 0] = tr[0]; T[lane * 4 + 1] = tr[1]; T[lane * 4 + 2] = tr[2];
-          __syncwarp();
-          {
-            const int k = lane >> 2, comp = lane & 3;
-            const int crow = ex->row[par][warp * 32 + 4 * k];
-            if (comp < 3 && crow >= 0) {
-              const float sum = (T[(4 * k) * 4 + comp] + T[(4 * k + 1) * 4 + comp]) + (T[(4 * k + 2) * 4 + comp] + T[(4 * k + 3) * 4 + comp]);
-              atomicAdd(reinterpret_cast<float*>(a.xagg) + (size_t)crow * 4 + comp, sum);
-            }
-          }
-          __syncwarp();
+        for (int k = 0; k < 3; ++k) {
+          const float d = ex->u.c.dir[par][k][r];
+          float t;
+          if (m == 0) t = a.use_tanh ? (d * tanhf(s)) * a.coords_range : d * s;       // coord_diff * tanh(phi) * range
+          else t = d * (a.use_tanh ? tanhf(s) * a.coords_range : s);                     // coord_cross * (tanh(phi_x) * range)
+          tr[k] = myrow >= 0 ? t : 0.f;
         }
+        // 4-row chunks belong to one receiver: lane = (chunk k, component) sums 4 rows and issues one RED
+        T[lane * 4 + 0] = tr[0]; T[lane * 4 + 1] = tr[1]; T[lane * 4 + 2] = tr[2];
+        __syncwarp();
+        {
+          const int k = lane >> 2, comp = lane & 3;
+          const int crow = ex->row[par][warp * 32 + 4 * k];
+          if (comp < 3 && crow >= 0) {
+            const float sum = (T[(4 * k) * 4 + comp] + T[(4 * k + 1) * 4 + comp]) + (T[(4 * k + 2) * 4 + comp] + T[(4 * k + 3) * 4 + comp]);
+            atomicAdd(reinterpret_cast<float*>(a.xagg) + (size_t)crow * 4 + comp, sum);
+          }
+        }
+        __syncwarp();
       }
       if (prof_on) {
         c3 = tc_clock();
         atomicAdd(&g_tc_prof[0], (unsigned long long)(c1 - c0));   // epilogue: waiting for scalars/accumulator
         atomicAdd(&g_tc_prof[1], (unsigned long long)(c2 - c1));   // pass 1
         atomicAdd(&g_tc_prof[2], (unsigned long long)(c3 - c2));   // pass 2 (GCL) / trans + chunk sums (coord)
-        atomicAdd(&g_tc_prof[3], 1ull);                            // virtual tiles
+        atomicAdd(&g_tc_prof[3], 1ull);                            // units
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&ctl->epi_done[acc]);
-        if (m == nm - 1) mbar_arrive(&ctl->scal_empty[par]);
+        mbar_arrive(&ctl->scal_empty[par]);
       }
     }
     if (!COORD && (tc_debug() & 512) && warp == 0 && lane == 0) {
-      atomicAdd(&g_tc_prof[14], (unsigned long long)(tc_clock() - ep0));     // epilogue warp 0: whole tile loop of this CTA
+      atomicAdd(&g_tc_prof[14], (unsigned long long)(tc_clock() - ep0));     // epilogue warp 0: whole loop of this CTA
       atomicAdd(&g_tc_prof[15], 1ull);
     }
   } else if (warp < MMA_WARP) {
     // ------------------------------------------------------------------------------------------ producers
-    // Thread mapping (coalesced gathers): producer warp pw owns tile rows [16 pw, 16 pw + 16); lane = (sub-row sr, piece p):
+    // Thread mapping (coalesced gathers): producer warp pw owns tile rows [16 pw, 16 pw + 16); lane = (sub-row sr, piece pc):
     // 8 lanes cover one row's contiguous 128 bytes (32 k-values), one LDG.128 instruction covers 4 rows = 4 L1 wavefronts.
-    // Step i handles rows 16 pw + 4 sr + i: the two rows of a half-warp differ in bit 2 of the row index, so their 64-byte
-    // pieces land in different halves of the 128B-swizzled row and the operand STS.64 are bank-conflict free.
-    // A thread handles 4 rows x 4 k per 32-k half.  The loop is seamless across MLPs and tiles: the gathers of the next
-    // 32-k step (same MLP, next MLP, or the first step of the next tile, whose scalars the scalar warps prepared while this
-    // tile was produced) are issued row by row as soon as the registers of the current step are consumed.
+    // A thread handles the 4-row chunk 16 pw + 4 sr + {0..3} x 4 k per 32-k half.  The chunk is one receiver (item 6 of DESIGN
+    // §2: segments are padded to 4 rows), so the receiver operand P[recv] is ONE load per half, not four; the four sender rows
+    // differ.  Within a half the two rows of a half-warp differ in bit 2 of the row index, so their 64-byte pieces land in
+    // different halves of the 128B-swizzled row and the operand STS.64 are bank-conflict free.
+    //
+    // Load scheduling around the proxy fence: fence.proxy.async (one per pipeline chunk, before the arrive) waits for every
+    // outstanding load of the thread, so a gather issued shortly before it delays the hand-off to the MMA thread by an L2
+    // round trip.  Gathers are therefore issued (i) for the second half of a chunk: row by row while the first half is being
+    // computed (they are consumed before the fence), (ii) for the first half of the NEXT chunk: into a second register set at
+    // the start of the current chunk's last half — a full half (~1 k cycles) before the fence, i.e. complete when it executes,
+    // (iii) across a unit boundary: right after the fence.
     const int ptid = threadIdx.x - EPI_WARPS * 32;
     const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
     const int dbg = tc_debug();
     const bool pprof = !COORD && (dbg & 512) && ptid == 0;
     uint32_t gc = 0;
     float pd2[4], pd0[4];
-    const float* Pa[4]; const float* Pb[4]; const float* tbp[4];
-    float4 ga[4], gb[4];
-    auto setup_tile = [&](int it) {
-      const int par = it % NSCAL;
-      mbar_wait(&ctl->scal_full[par], (uint32_t)(it / NSCAL) & 1u);
+    const float* const Pt = a.P + 4 * pc;      // this thread's 16-byte piece of a P row; rows/blocks are added per load
+    int prow = 0, pcol[4] = {0, 0, 0, 0}, pty[4] = {0, 0, 0, 0};
+    int moff = 0;                              // column offset of the unit's MLP inside the receiver / sender blocks
+    const int soff = nm * H;                // sender block follows the nm receiver blocks
+    float4 ga, gb[4], ga2, gb2[4];
+    auto setup_unit = [&](int j) {             // row indices and scalars of unit j; returns its MLP index
+      int m;
+      unit_tile(j, m);
+      const int par = j % NSCAL;
+      mbar_wait(&ctl->scal_full[par], (uint32_t)(j / NSCAL) & 1u);
+      const int r0 = 16 * pw + 4 * sr;
+      prow = max(ex->row[par][r0], 0);
+      moff = m * H;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = 16 * pw + 4 * sr + i;
-        const int prow = ex->row[par][r] < 0 ? 0 : ex->row[par][r];
-        Pa[i] = a.P + (size_t)prow * a.ldp + 4 * pc;                                  // receiver block (+ m*H per MLP)
-        Pb[i] = a.P + (size_t)ex->col[par][r] * a.ldp + nm * H256 + 4 * pc;           // sender block
-        pd2[i] = ex->d2[par][r]; pd0[i] = ex->d0[par][r];
-        tbp[i] = has_tb ? a.tb[0] + ex->type[par][r] * H256 + 4 * pc : nullptr;
+        pcol[i] = ex->col[par][r0 + i];
+        pd2[i] = ex->d2[par][r0 + i]; pd0[i] = ex->d0[par][r0 + i];
+        if (has_tb) pty[i] = ex->type[par][r0 + i] * H;
       }
+      return m;
     };
-    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc_wait = 0, acc_store = 0, acc_comp = 0, acc_fence = 0;
-    const long long pp0 = pprof ? tc_clock() : 0;
-    if (pprof) t0 = tc_clock();
-    setup_tile(0);
+    auto recv_ptr = [&](int hf) { return Pt + (size_t)prow * a.ldp + (moff + hf * TKC); };
+    auto send_ptr = [&](int i, int hf) { return Pt + (size_t)pcol[i] * a.ldp + (soff + moff + hf * TKC); };
+    const bool no_gather = (dbg & 64) != 0;        // instrumented builds only: operands from registers instead of L2
+    auto ld4 = [&](const float* p) { return no_gather ? make_float4(0.1f, -0.2f, 0.3f, 0.05f) : *reinterpret_cast<const float4*>(p); };
+    auto issue = [&](int hf, float4& xa, float4 (&xb)[4]) {
+      xa = ld4(recv_ptr(hf));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ga[i] = *reinterpret_cast<const float4*>(Pa[i]);
-      gb[i] = *reinterpret_cast<const float4*>(Pb[i]);
-    }
-    if (pprof) atomicAdd(&g_tc_prof[8], (unsigned long long)(tc_clock() - t0));      // first tile: scalars + first gathers issued
-    for (int it = 0; it < n_my_tiles; ++it) {
-      for (int m = 0; m < nm; ++m) {
-        const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H256;
-        const size_t tb_off = has_tb ? (size_t)(a.tb[m] - a.tb[0]) : 0;
-#pragma unroll kPUnroll
-        for (int hf = 0; hf < halves; ++hf) {
-          const int s = gc & 1;
-          const bool same = hf + 1 < halves;
-          float4 v[4];
-          if (pprof) t0 = tc_clock();
-          if (dbg & 2) {
-            v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else {
+      for (int i = 0; i < 4; ++i) xb[i] = ld4(send_ptr(i, hf));
+    };
+    long long t0 = 0, t1 = 0, t2 = 0, acc_wait = 0, acc_comp = 0, acc_fence = 0;
+    const long long pp0 = pprof ? tc_clock() : 0;
+    int m = setup_unit(0);
+    issue(0, ga, gb);
+    for (int j = 0; j < n_my; ++j) {
+      const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H;
+      const float* tbm = has_tb ? a.tb[m] + 4 * pc : nullptr;
+#pragma unroll 1
+      for (int kc = 0; kc < chunks; ++kc) {
+        const int s = gc & 1;
+        char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
+        if (pprof) t0 = tc_clock();
+        mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);      // stage released by the MMAs that read it two chunks ago
+        if (pprof) { t1 = tc_clock(); acc_wait += t1 - t0; }
+#pragma unroll
+        for (int h = 0; h < HPC; ++h) {
+          const int hf = kc * HPC + h;
+          const bool last_half = (h == HPC - 1);
+          if (last_half && kc + 1 < chunks && !(dbg & 2)) issue(hf + 1, ga2, gb2);          // (ii)
+          if (!(dbg & 2)) {
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
+            const f32x2 a01 = pk2(ga.x, ga.y), a23 = pk2(ga.z, ga.w);
+            if (!last_half) ga = ld4(recv_ptr(hf + 1));        // (i)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const f32x2 d2p = pk2(pd2[i], pd2[i]), d0p = pk2(pd0[i], pd0[i]);
-              f32x2 u01 = fma2(d0p, pk2(r04.x, r04.y), fma2(d2p, pk2(r4.x, r4.y), add2(pk2(ga[i].x, ga[i].y), pk2(gb[i].x, gb[i].y))));
-              f32x2 u23 = fma2(d0p, pk2(r04.z, r04.w), fma2(d2p, pk2(r4.z, r4.w), add2(pk2(ga[i].z, ga[i].w), pk2(gb[i].z, gb[i].w))));
-              if (same) {     // registers of row i are free: issue its gathers of the next step right away
-                ga[i] = *reinterpret_cast<const float4*>(Pa[i] + m * H256 + (hf + 1) * TKC);
-                gb[i] = *reinterpret_cast<const float4*>(Pb[i] + m * H256 + (hf + 1) * TKC);
-              }
+              f32x2 u01 = fma2(d0p, pk2(r04.x, r04.y), fma2(d2p, pk2(r4.x, r4.y), add2(a01, pk2(gb[i].x, gb[i].y))));
+              f32x2 u23 = fma2(d0p, pk2(r04.z, r04.w), fma2(d2p, pk2(r4.z, r4.w), add2(a23, pk2(gb[i].z, gb[i].w))));
+              if (!last_half) gb[i] = ld4(send_ptr(i, hf + 1));   // (i): registers of row i are free
               if (has_tb) {
-                const float4 t4 = *reinterpret_cast<const float4*>(tbp[i] + tb_off + hf * TKC);
+                const float4 t4 = *reinterpret_cast<const float4*>(tbm + pty[i] + hf * TKC);
                 u01 = add2(u01, pk2(t4.x, t4.y)); u23 = add2(u23, pk2(t4.z, t4.w));
               }
-              u01 = silu2(u01); u23 = silu2(u23);
-              upk2(u01, v[i].x, v[i].y); upk2(u23, v[i].z, v[i].w);
-            }
-            if (!same) {
-              if (m + 1 < nm) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  ga[i] = *reinterpret_cast<const float4*>(Pa[i] + (m + 1) * H256);
-                  gb[i] = *reinterpret_cast<const float4*>(Pb[i] + (m + 1) * H256);
-                }
-              } else if (it + 1 < n_my_tiles) {
-                setup_tile(it + 1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  ga[i] = *reinterpret_cast<const float4*>(Pa[i]);
-                  gb[i] = *reinterpret_cast<const float4*>(Pb[i]);
-                }
-              }
+              if (!(dbg & 128)) { u01 = silu2(u01); u23 = silu2(u23); }      // 128: instrumented builds only
+              float4 v;
+              upk2(u01, v.x, v.y); upk2(u23, v.z, v.w);
+              store_piece<F16>(st, 16 * pw + 4 * sr + i, hf, pc, v);
             }
           }
-          if (pprof) { t1 = tc_clock(); acc_comp += t1 - t0; }
-          if (!F16 || !(hf & 1)) mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);
-          if (pprof) { t2 = tc_clock(); acc_wait += t2 - t1; }
-          if (!(dbg & 2)) {
-            char* st = cv.stages + (size_t)s * STAGE_BYTES;
+        }
+        if (pprof) { t2 = tc_clock(); acc_comp += t2 - t1; }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+        ++gc;
+        if (pprof) acc_fence += tc_clock() - t2;
+        if (kc + 1 < chunks) {
+          ga = ga2;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) store_piece<F16>(st, 16 * pw + 4 * sr + i, hf, pc, v[i]);
-          }
-          if (pprof) { t3 = tc_clock(); acc_store += t3 - t2; }
-          if (!F16 || (hf & 1)) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->full_x[s]);
-            ++gc;
-          }
-          if (pprof) acc_fence += tc_clock() - t3;
+          for (int i = 0; i < 4; ++i) gb[i] = gb2[i];
         }
-        if (pprof) {
-          atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU + issue of next gathers (+ next-tile setup)
-          atomicAdd(&g_tc_prof[10], (unsigned long long)acc_wait);   // waiting for the stage to be released by the MMAs
-          atomicAdd(&g_tc_prof[11], (unsigned long long)acc_store);  // split + swizzled stores
-          atomicAdd(&g_tc_prof[12], (unsigned long long)acc_fence);  // fence.proxy.async + arrive
-          atomicAdd(&g_tc_prof[13], 1ull);
-          acc_comp = acc_wait = acc_store = acc_fence = 0;
-        }
+      }
+      if (j + 1 < n_my) {                                                                      // (iii)
+        m = setup_unit(j + 1);
+        if (!(dbg & 2)) issue(0, ga, gb);
+      }
+      if (pprof) {
+        atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU + split + swizzled stores
+        atomicAdd(&g_tc_prof[10], (unsigned long long)acc_wait);   // waiting for the stage to be released by the MMAs
+        atomicAdd(&g_tc_prof[12], (unsigned long long)acc_fence);  // fence.proxy.async + arrive
+        atomicAdd(&g_tc_prof[13], 1ull);
+        acc_comp = acc_wait = acc_fence = 0;
       }
     }
     if (pprof) {
@@ -950,28 +958,30 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       atomicAdd(&g_tc_prof[25], 1ull);
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role<F16>(ctl, cv.stages, n_my, chunks, COORD ? 2 : 1);
+    if (lane == 0) mma_role<F16, H>(ctl, cv.stages, n_my, chunks, COORD ? 2 : 1);
     __syncwarp();
   } else if (warp == TMA_WARP) {
     if (lane == 0) {
       uint32_t gc = 0;
-      for (int vt = 0; vt < n_my; ++vt) {
-        const int m = vt % nm;
-        tma_role(ctl, cv.stages, a.W2hi[m], a.W2lo[m], gc, chunks);
+      for (int j = 0; j < n_my; ++j) {
+        int m;
+        unit_tile(j, m);
+        tma_role<H>(ctl, cv.stages, a.W2hi[m], a.W2lo[m], gc, chunks);
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------------ scalar warps
     // 64 threads, two edges each: erow/ecol -> x[r], x[c] (-> centroid) is a chain of dependent global loads; running it
-    // one tile ahead (double-buffered by tile parity) keeps it off the producers' critical path.
+    // one unit ahead (NSCAL buffer sets) keeps it off the producers' critical path.
     const int st = threadIdx.x - (TMA_WARP + 1) * 32;
-    for (int it = 0; it < n_my_tiles; ++it) {
-      const int par = it % NSCAL;
-      const int e0 = (blockIdx.x + it * gridDim.x) * TM;
-      mbar_wait(&ctl->scal_empty[par], ((uint32_t)(it / NSCAL) & 1u) ^ 1u);   // epilogue finished the tile that last used this set
-      edge_scalars<COORD>(a, ex, par, st, e0, E);
-      edge_scalars<COORD>(a, ex, par, st + SCAL_WARPS * 32, e0, E);
+    for (int j = 0; j < n_my; ++j) {
+      const int par = j % NSCAL;
+      int m;
+      const int e0 = unit_tile(j, m) * TM;
+      mbar_wait(&ctl->scal_empty[par], ((uint32_t)(j / NSCAL) & 1u) ^ 1u);   // epilogue finished the unit that last used this set
+      edge_scalars<COORD, H>(a, ex, par, st, e0, E, m);
+      edge_scalars<COORD, H>(a, ex, par, st + SCAL_WARPS * 32, e0, E, m);
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->scal_full[par]);
     }
@@ -982,32 +992,48 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
 // =====================================================================================================
 // launchers
 // =====================================================================================================
-static size_t gemm_smem_bytes() { return kTcSmemBase + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE; }
-static size_t edge_smem_bytes() { return kTcSmemBase + sizeof(EdgeExtra); }
+template <int H> static size_t gemm_smem_bytes() { return tc_smem_base<H>() + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE; }
+template <int H> static size_t edge_smem_bytes() { return tc_smem_base<H>() + sizeof(EdgeExtra<H>); }
 
-int configure_tc_kernels() {
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes()));
-  return 0;
+bool tc_width_supported(int H) { return H == 128 || H == 192 || H == 256; }
+
+// run `fn.template operator()<H>()` for the run-time width
+template <typename Fn>
+static int dispatch_width(int H, Fn&& fn) {
+  switch (H) {
+    case 128: return fn.template operator()<128>();
+    case 192: return fn.template operator()<192>();
+    case 256: return fn.template operator()<256>();
+    default: set_error("tensor-core kernels exist for hidden_nf 128, 192, 256 (got %d)", H); return DSB_ERR_UNSUPPORTED_CONFIG;
+  }
+}
+
+int configure_tc_kernels(int H) {
+  return dispatch_width(H, [&]<int W>() -> int {
+    const int gs = (int)gemm_smem_bytes<W>(), es = (int)edge_smem_bytes<W>();
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    return 0;
+  });
 }
 
 int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage& w, int n_tile_off, bool f16, int32_t* status,
                         cudaStream_t s) {
   if (g.M == 0) return 0;
-  const int K = g.K1 + g.K2;
+  const int K = g.K1 + g.K2, TN = d->cfg.hidden_nf;
   if ((g.Nn % TN) || (K % TKC16) || (g.K1 % TKC16) || (g.lda1 % 4) || (g.ldc % 4)) {
     set_error("tc_node_gemm: unsupported shape K1=%d K2=%d Nn=%d", g.K1, g.K2, g.Nn);
     return DSB_ERR_INVALID_ARGUMENT;
   }
   TcGemmArgs a;
   a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2;
-  const size_t img_off = (size_t)n_tile_off * (K / (f16 ? TKC16 : TKC)) * B_CHUNK_FLOATS;     // skip the first n-tiles of the image
+  const size_t img_off = (size_t)n_tile_off * (K / (f16 ? TKC16 : TKC)) * (size_t)(TN * TKC);     // skip the first n-tiles of the image
   a.Bhi = (f16 ? w.h_hi : w.t_hi) + img_off; a.Blo = (f16 ? w.h_lo : w.t_lo) + img_off;
   a.Z = g.Z; a.ldz = g.ldz;
   a.dead_nt = g.dead_cols / TN; a.dead_mt = a.dead_nt > 0 ? (g.dead_rows_from + TM - 1) / TM : 0;
@@ -1017,8 +1043,10 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
   const int dmt_ = a.dead_nt > 0 ? (a.dead_mt < ntm_ ? a.dead_mt : ntm_) : ntm_;
   const int n_tiles = dmt_ * ntn_ + (ntm_ - dmt_) * (ntn_ - a.dead_nt);
   const int grid = n_tiles < d->num_sms ? n_tiles : d->num_sms;
-  DSB_CUDA_OK(launch_k(f16 ? tc_node_gemm_kernel<true> : tc_node_gemm_kernel<false>, grid, TC_THREADS, gemm_smem_bytes(), s, a));
-  return 0;
+  return dispatch_width(TN, [&]<int W>() -> int {
+    DSB_CUDA_OK(launch_k(f16 ? tc_node_gemm_kernel<true, W> : tc_node_gemm_kernel<false, W>, grid, TC_THREADS, gemm_smem_bytes<W>(), s, a));
+    return 0;
+  });
 }
 
 int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, bool f16, int32_t* status, cudaStream_t s) {
@@ -1033,8 +1061,10 @@ int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   a.hout = ws.h; a.zero = ws.agg; a.M = dm.N; a.status = status;
   const int ntm = (dm.N + TM - 1) / TM;
   const int grid = ntm < d->num_sms ? ntm : d->num_sms;
-  DSB_CUDA_OK(launch_k(f16 ? tc_node_mlp_kernel<true> : tc_node_mlp_kernel<false>, grid, TC_THREADS, gemm_smem_bytes(), s, a));
-  return 0;
+  return dispatch_width(H, [&]<int W>() -> int {
+    DSB_CUDA_OK(launch_k(f16 ? tc_node_mlp_kernel<true, W> : tc_node_mlp_kernel<false, W>, grid, TC_THREADS, gemm_smem_bytes<W>(), s, a));
+    return 0;
+  });
 }
 
 int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const float4* x, PView pv, bool f16,
@@ -1046,9 +1076,11 @@ int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   a.inv_scale[0] = f16 ? w.iW2.h_inv : 1.0f; a.inv_scale[1] = 1.0f;
   a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
   a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg; a.status = status;
-  DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<false, true> : tc_edge_kernel<false, false>, d->num_sms, EDGE_THREADS, edge_smem_bytes(), s, a));
-  DSB_CUDA_OK(cudaGetLastError());
-  return 0;
+  return dispatch_width(d->cfg.hidden_nf, [&]<int W>() -> int {
+    DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<false, true, W> : tc_edge_kernel<false, false, W>, d->num_sms, EDGE_THREADS,
+                         edge_smem_bytes<W>(), s, a));
+    return 0;
+  });
 }
 
 int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const EquivW& w, const float4* x, PView pv, bool f16,
@@ -1066,9 +1098,11 @@ int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace&
   }
   a.wa = w.w3; a.ba = nullptr;
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg; a.status = status;
-  DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<true, true> : tc_edge_kernel<true, false>, d->num_sms, EDGE_THREADS, edge_smem_bytes(), s, a));
-  DSB_CUDA_OK(cudaGetLastError());
-  return 0;
+  return dispatch_width(c.hidden_nf, [&]<int W>() -> int {
+    DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<true, true, W> : tc_edge_kernel<true, false, W>, d->num_sms, EDGE_THREADS,
+                         edge_smem_bytes<W>(), s, a));
+    return 0;
+  });
 }
 
 }  // namespace dsb

@@ -22,15 +22,26 @@ namespace dsb {
 namespace tc {
 
 constexpr int TM = 128;            // rows (edges / nodes) per tile = TMEM lanes
-constexpr int TN = 256;            // accumulator columns per tile
 constexpr int TKC = 32;            // k-values per 128-byte swizzle row with 4-byte (TF32) operands
 constexpr int TKC16 = 64;          // ... with 2-byte (FP16) operands
 constexpr float X_SCALE = 1.0f;    // 3xFP16 activation scale (1: |x| < 0.25 has a subnormal fp16 residual, abs. error <= 3e-8)
 constexpr int A_CHUNK_BYTES = TM * 128;        // 16 KB
-constexpr int B_CHUNK_BYTES = TN * 128;        // 32 KB
-constexpr int B_CHUNK_FLOATS = TN * TKC;       // 8192
-constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES + 2 * B_CHUNK_BYTES;   // Xhi, Xlo, Whi, Wlo = 96 KB
 constexpr int NSTAGE = 2;
+constexpr int ACC_STRIDE = 256;    // TMEM column offset of the second accumulator (512 columns are allocated for every width)
+
+// Geometry that depends on the width H = hidden_nf of the network (128, 192 or 256): the accumulator tile is TM x H, a weight
+// chunk image is H rows x 128 B.
+template <int H>
+struct Geo {
+  static_assert(H == 128 || H == 192 || H == 256, "tensor-core kernels are built for hidden_nf 128, 192, 256");
+  static constexpr int TN = H;                                  // accumulator columns per tile = N of one MMA
+  static constexpr int B_CHUNK_BYTES = H * 128;                 // 16 / 24 / 32 KB
+  static constexpr int B_CHUNK_FLOATS = H * TKC;                // 32-bit words per chunk image
+  static constexpr int STAGE_BYTES = 2 * A_CHUNK_BYTES + 2 * B_CHUNK_BYTES;   // Xhi, Xlo, Whi, Wlo = 64 / 80 / 96 KB
+  // instruction descriptor: D=F32, K-major both, N=H, M=128  (cute::UMMA::InstrDescriptor bit layout); A=B=TF32 (code 2) / F16 (0)
+  static constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  static constexpr uint32_t IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+};
 
 constexpr int EPI_WARPS = 4;       // warps 0..3  (warp w owns TMEM lanes 32w..32w+31)
 constexpr int PROD_WARPS = 8;      // warps 4..11
@@ -38,11 +49,6 @@ constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;        // 12
 constexpr int TMA_WARP = MMA_WARP + 1;                  // 13
 constexpr int TC_THREADS = (TMA_WARP + 1) * 32;         // 448
 constexpr int PROD_THREADS = PROD_WARPS * 32;           // 256
-
-// instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128  (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t IDESC_TF32_M128_N256 = (1u << 4) | (2u << 7) | (2u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
-// same with A=B=F16 (format code 0)
-constexpr uint32_t IDESC_F16_M128_N256 = (1u << 4) | (0u << 7) | (0u << 10) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -280,26 +286,27 @@ __device__ __forceinline__ int tc_debug() {
 __device__ unsigned long long g_tc_prof[64];
 __device__ __forceinline__ long long tc_clock() { return clock64(); }
 // the 12 MMAs of one K-chunk held in stage memory `st` (A_hi | A_lo | W_hi | W_lo): 4 k-steps x 3 split products into d
-template <bool F16>
+template <bool F16, int H>
 __device__ __forceinline__ void mma_issue_chunk(uint32_t d, char* st, bool first_chunk) {
-  const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + B_CHUNK_BYTES;
+  using G = Geo<H>;
+  const uint32_t xhi = smem_u32(st), xlo = xhi + A_CHUNK_BYTES, whi = xhi + 2 * A_CHUNK_BYTES, wlo = whi + G::B_CHUNK_BYTES;
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {       // 4 k-steps of 32 bytes per 128-byte row (K=8 tf32 or K=16 fp16 each)
     const uint32_t ko = ks * 32;
     const uint32_t acc = (first_chunk && ks == 0) ? 0u : 1u;
     if constexpr (F16) {
-      umma_f16(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, acc);
-      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_F16_M128_N256, 1u);
-      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_F16_M128_N256, 1u);
+      umma_f16(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), G::IDESC_F16, acc);
+      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), G::IDESC_F16, 1u);
+      umma_f16(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), G::IDESC_F16, 1u);
     } else {
-      umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, acc);
-      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC_TF32_M128_N256, 1u);
-      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC_TF32_M128_N256, 1u);
+      umma_tf32(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), G::IDESC_TF32, acc);
+      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), G::IDESC_TF32, 1u);
+      umma_tf32(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), G::IDESC_TF32, 1u);
     }
   }
 }
 
-template <bool F16>
+template <bool F16, int H>
 __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_tiles, int chunks_per_tile, int tag) {
   const uint32_t tmem = ctl->tmem_base;
   const bool skip = (tc_debug() & 8) != 0;
@@ -314,7 +321,7 @@ __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_ti
     mbar_wait(&ctl->epi_done[a], ((it >> 1) & 1) ^ 1);      // accumulator buffer drained by the epilogue
     tc_fence_after();
     if (mprof) w_acc += tc_clock() - q0;
-    const uint32_t d = tmem + (uint32_t)(a * TN);
+    const uint32_t d = tmem + (uint32_t)(a * ACC_STRIDE);
     for (int kc = 0; kc < chunks_per_tile; ++kc, ++g) {
       const int s = g & 1;
       const uint32_t par = (g >> 1) & 1;
@@ -324,7 +331,7 @@ __device__ __forceinline__ void mma_role(Control* ctl, char* stages, int n_my_ti
       mbar_wait(&ctl->full_x[s], par);
       tc_fence_after();
       if (mprof) { q2 = tc_clock(); w_w += q1 - q0; w_x += q2 - q1; }
-      if (!skip) mma_issue_chunk<F16>(d, stages + (size_t)s * STAGE_BYTES, kc == 0);
+      if (!skip) mma_issue_chunk<F16, H>(d, stages + (size_t)s * Geo<H>::STAGE_BYTES, kc == 0);
       umma_commit(&ctl->empty[s]);          // stage reusable once these MMAs have read it
       if (mprof) { q3 = tc_clock(); w_iss += q3 - q2; }
     }

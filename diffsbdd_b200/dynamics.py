@@ -151,7 +151,7 @@ class EGNNDynamics(nn.Module):
         self.defer_status_check = False    # samplers that CUDA-graph the loop check once at the end
         # arithmetic path: bitmask 1 node GEMMs | 2 edge kernel | 4 coordinate kernel on tcgen05, 8 = 3xFP16 operand split
         # instead of 3xTF32; 0 = fp32 FFMA kernels.  Names: 'fp32' (0), '3xtf32' (7), '3xfp16' (15).
-        # 'auto' = '3xfp16' when hidden_nf == 256 (the only width with tensor-core kernels), else 'fp32'.
+        # 'auto' = '3xfp16' when hidden_nf is 128, 192 or 256 (the widths with tensor-core kernels), else 'fp32'.
         self._math_mode = os.environ.get('DSB_MATH_MODE', 'auto')
         self.to(device)
 
@@ -175,7 +175,7 @@ class EGNNDynamics(nn.Module):
     def math_mode(self) -> int:
         m = self._math_mode
         if m in ('auto', None):
-            return 15 if self.cfg.hidden_nf == 256 else 0
+            return 15 if self.cfg.hidden_nf in (128, 192, 256) else 0
         if m == 'fp32':
             return 0
         if m == '3xtf32':
