@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = (
     'dsb_param_count', 'dsb_param_name', 'dsb_dynamics_create', 'dsb_dynamics_destroy',
     'dsb_edge_capacity', 'dsb_dynamics_workspace_bytes', 'dsb_dynamics_forward', 'dsb_dynamics_edges',
     'dsb_dynamics_last_launch_count', 'dsb_set_programmatic_launch', 'dsb_dynamics_set_math_mode', 'dsb_dynamics_set_profiling', 'dsb_dynamics_collect_profile',
-    'dsb_ddpm_ligand_update', 'dsb_ddpm_inpaint_update', 'dsb_last_error', 'dsb_version', 'dsb_debug_set_tc_flags', 'dsb_debug_read_tc_prof',
+    'dsb_ddpm_ligand_update', 'dsb_ddpm_inpaint_update', 'dsb_ddpm_joint_update', 'dsb_ddpm_joint_inpaint_update', 'dsb_last_error', 'dsb_version', 'dsb_debug_set_tc_flags', 'dsb_debug_read_tc_prof',
 )
 
 
@@ -95,6 +95,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.dsb_ddpm_ligand_update.restype = C.c_int
     lib.dsb_ddpm_inpaint_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp]
     lib.dsb_ddpm_inpaint_update.restype = C.c_int
+    lib.dsb_ddpm_joint_update.argtypes = [vp] * 10 + [i64, i64, i64, i32, i32, vp]
+    lib.dsb_ddpm_joint_update.restype = C.c_int
+    lib.dsb_ddpm_joint_inpaint_update.argtypes = [vp] * 15 + [i64, i64, i64, i32, i32, vp]
+    lib.dsb_ddpm_joint_inpaint_update.restype = C.c_int
     _LIB = lib
     return lib
 

@@ -489,6 +489,154 @@ __global__ void __launch_bounds__(128) ddpm_inpaint_kernel(float* z, float* pock
   }
 }
 
+
+// ---- joint model (EnVariationalDiffusion): fused reverse update and fused RePaint iteration ---------------------------
+// Node n of graph g: ligand rows [l0, l1) of the ligand tensors, pocket rows [p0, p1) of the pocket tensors.  The position
+// noise nx is ONE tensor [NL + NP, 3] (ligand rows first), as sample_center_gravity_zero_gaussian_batch draws it
+// (en_diffusion.py:559-578); its per-graph mean over ligand+pocket nodes is removed before use (en_diffusion.py:940-944).
+struct JointSpan { int l0, l1, p0, p1; float n; };
+__device__ __forceinline__ JointSpan joint_span(const int64_t* mask_atoms, const int64_t* mask_res, int NL, int NP, int g) {
+  JointSpan s;
+  s.l0 = lb64(mask_atoms, NL, g); s.l1 = lb64(mask_atoms, NL, (int64_t)g + 1);
+  s.p0 = lb64(mask_res, NP, g); s.p1 = lb64(mask_res, NP, (int64_t)g + 1);
+  const int cnt = (s.l1 - s.l0) + (s.p1 - s.p0);
+  s.n = cnt > 0 ? (float)cnt : 1.f;
+  return s;
+}
+// per-graph mean of the position noise rows
+__device__ __forceinline__ void joint_noise_mean(const float* nx, const JointSpan& sp, int NL, float (*red)[4], float* mean) {
+  float v[3] = {0.f, 0.f, 0.f};
+  for (int i = sp.l0 + threadIdx.x; i < sp.l1; i += blockDim.x) { v[0] += nx[i * 3]; v[1] += nx[i * 3 + 1]; v[2] += nx[i * 3 + 2]; }
+  for (int i = sp.p0 + threadIdx.x; i < sp.p1; i += blockDim.x) {
+    const size_t r = (size_t)(NL + i) * 3; v[0] += nx[r]; v[1] += nx[r + 1]; v[2] += nx[r + 2];
+  }
+  block_sum(v, 3, red);
+  mean[0] = v[0] / sp.n; mean[1] = v[1] / sp.n; mean[2] = v[2] / sp.n;
+}
+
+// EnVariationalDiffusion.sample_p_zs_given_zt without the denoiser call (en_diffusion.py:503-557):
+//   mu = z / alpha_ts - coef * eps_hat ; z' = mu + sigma * eps (eps.x COM-free over ligand+pocket) ; joint COM of z'.x removed.
+__global__ void __launch_bounds__(128) ddpm_joint_update_kernel(float* z_lig, float* z_poc, const float* __restrict__ eps_lig,
+                                                                 const float* __restrict__ eps_poc, const float* __restrict__ nx,
+                                                                 const float* __restrict__ nhl, const float* __restrict__ nhp,
+                                                                 const float* __restrict__ coef, const int64_t* __restrict__ mask_atoms,
+                                                                 const int64_t* __restrict__ mask_res, int NL, int NP, int A, int R) {
+  const int g = blockIdx.x;
+  const JointSpan sp = joint_span(mask_atoms, mask_res, NL, NP, g);
+  const int D = 3 + A, DR = 3 + R;
+  const float alpha = coef[g * 3 + 0], cb = coef[g * 3 + 1], sigma = coef[g * 3 + 2];
+  __shared__ float red[9][4];
+  float nm[3];
+  joint_noise_mean(nx, sp, NL, red, nm);
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int idx = sp.l0 * D + threadIdx.x; idx < sp.l1 * D; idx += blockDim.x) {
+    const int c = idx % D, i = idx / D;
+    const float e = c < 3 ? nx[(size_t)i * 3 + c] - nm[c] : nhl[(size_t)i * A + (c - 3)];
+    const float v = (z_lig[idx] / alpha - cb * eps_lig[idx]) + sigma * e;
+    z_lig[idx] = v;
+    if (c < 3) s[c] += v;
+  }
+  for (int idx = sp.p0 * DR + threadIdx.x; idx < sp.p1 * DR; idx += blockDim.x) {
+    const int c = idx % DR, i = idx / DR;
+    const float e = c < 3 ? nx[(size_t)(NL + i) * 3 + c] - nm[c] : nhp[(size_t)i * R + (c - 3)];
+    const float v = (z_poc[idx] / alpha - cb * eps_poc[idx]) + sigma * e;
+    z_poc[idx] = v;
+    if (c < 3) s[c] += v;
+  }
+  block_sum(s, 3, red);
+  const float m0 = s[0] / sp.n, m1 = s[1] / sp.n, m2 = s[2] / sp.n;
+  __syncthreads();
+  for (int i = sp.l0 + threadIdx.x; i < sp.l1; i += blockDim.x) {
+    z_lig[(size_t)i * D] -= m0; z_lig[(size_t)i * D + 1] -= m1; z_lig[(size_t)i * D + 2] -= m2;
+  }
+  for (int i = sp.p0 + threadIdx.x; i < sp.p1; i += blockDim.x) {
+    z_poc[(size_t)i * DR] -= m0; z_poc[(size_t)i * DR + 1] -= m1; z_poc[(size_t)i * DR + 2] -= m2;
+  }
+}
+
+// One RePaint iteration of EnVariationalDiffusion.inpaint after the reverse step (en_diffusion.py:741-807), in place on
+// (z_lig, z_poc) = the denoised "unknown" sample:
+//   z_known = alpha_s xh0 + sigma_s eps1 (eps1.x COM-free)                                  (noised_representation, :302-317)
+//   shift   = COM_fixed(z_unknown) - COM_fixed(z_known) over the fixed ligand+pocket nodes ; z_known.x += shift   (:751-772)
+//   z       = z_known * fixed + z_unknown * (1 - fixed)                                       (:774-775)
+//   if nx3: z = alpha_ts z + sigma_ts eps3 (eps3.x COM-free), joint COM of z.x removed        (sample_p_zt_given_zs, :479-501, :790-807)
+__global__ void __launch_bounds__(128) ddpm_joint_inpaint_kernel(
+    float* z_lig, float* z_poc, const float* __restrict__ x0_lig, const float* __restrict__ x0_poc, const float* __restrict__ fix_lig,
+    const float* __restrict__ fix_poc, const float* __restrict__ nx1, const float* __restrict__ nhl1, const float* __restrict__ nhp1,
+    const float* __restrict__ nx3, const float* __restrict__ nhl3, const float* __restrict__ nhp3, const float* __restrict__ coef,
+    const int64_t* __restrict__ mask_atoms, const int64_t* __restrict__ mask_res, int NL, int NP, int A, int R) {
+  const int g = blockIdx.x;
+  const JointSpan sp = joint_span(mask_atoms, mask_res, NL, NP, g);
+  const int D = 3 + A, DR = 3 + R;
+  const float alpha_s = coef[g * 4 + 0], sigma_s = coef[g * 4 + 1], alpha_ts = coef[g * 4 + 2], sigma_ts = coef[g * 4 + 3];
+  __shared__ float red[9][4];
+  float n1[3];
+  joint_noise_mean(nx1, sp, NL, red, n1);
+  auto zk_lig = [&](int idx, int c, int i) {
+    const float e = c < 3 ? nx1[(size_t)i * 3 + c] - n1[c] : nhl1[(size_t)i * A + (c - 3)];
+    return alpha_s * x0_lig[idx] + sigma_s * e;
+  };
+  auto zk_poc = [&](int idx, int c, int i) {
+    const float e = c < 3 ? nx1[(size_t)(NL + i) * 3 + c] - n1[c] : nhp1[(size_t)i * R + (c - 3)];
+    return alpha_s * x0_poc[idx] + sigma_s * e;
+  };
+  // COM of the fixed nodes: denoised vs. noised
+  float v[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int idx = sp.l0 * D + threadIdx.x; idx < sp.l1 * D; idx += blockDim.x) {
+    const int c = idx % D, i = idx / D;
+    if (c < 3 && fix_lig[i] != 0.f) { v[c] += z_lig[idx]; v[3 + c] += zk_lig(idx, c, i); if (c == 0) v[6] += 1.f; }
+  }
+  for (int idx = sp.p0 * DR + threadIdx.x; idx < sp.p1 * DR; idx += blockDim.x) {
+    const int c = idx % DR, i = idx / DR;
+    if (c < 3 && fix_poc[i] != 0.f) { v[c] += z_poc[idx]; v[3 + c] += zk_poc(idx, c, i); if (c == 0) v[6] += 1.f; }
+  }
+  block_sum(v, 7, red);
+  const float nf = v[6] > 0.f ? v[6] : 1.f;
+  float shift[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) shift[c] = v[c] / nf - v[3 + c] / nf;
+  float n3[3] = {0.f, 0.f, 0.f};
+  if (nx3) joint_noise_mean(nx3, sp, NL, red, n3);
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int idx = sp.l0 * D + threadIdx.x; idx < sp.l1 * D; idx += blockDim.x) {
+    const int c = idx % D, i = idx / D;
+    float zk = zk_lig(idx, c, i);
+    if (c < 3) zk += shift[c];
+    const float f = fix_lig[i];
+    float o = zk * f + z_lig[idx] * (1.f - f);
+    if (nx3) {
+      const float e = c < 3 ? nx3[(size_t)i * 3 + c] - n3[c] : nhl3[(size_t)i * A + (c - 3)];
+      o = alpha_ts * o + sigma_ts * e;
+      if (c < 3) s[c] += o;
+    }
+    z_lig[idx] = o;
+  }
+  for (int idx = sp.p0 * DR + threadIdx.x; idx < sp.p1 * DR; idx += blockDim.x) {
+    const int c = idx % DR, i = idx / DR;
+    float zk = zk_poc(idx, c, i);
+    if (c < 3) zk += shift[c];
+    const float f = fix_poc[i];
+    float o = zk * f + z_poc[idx] * (1.f - f);
+    if (nx3) {
+      const float e = c < 3 ? nx3[(size_t)(NL + i) * 3 + c] - n3[c] : nhp3[(size_t)i * R + (c - 3)];
+      o = alpha_ts * o + sigma_ts * e;
+      if (c < 3) s[c] += o;
+    }
+    z_poc[idx] = o;
+  }
+  if (nx3) {
+    block_sum(s, 3, red);
+    const float m0 = s[0] / sp.n, m1 = s[1] / sp.n, m2 = s[2] / sp.n;
+    __syncthreads();
+    for (int i = sp.l0 + threadIdx.x; i < sp.l1; i += blockDim.x) {
+      z_lig[(size_t)i * D] -= m0; z_lig[(size_t)i * D + 1] -= m1; z_lig[(size_t)i * D + 2] -= m2;
+    }
+    for (int i = sp.p0 + threadIdx.x; i < sp.p1; i += blockDim.x) {
+      z_poc[(size_t)i * DR] -= m0; z_poc[(size_t)i * DR + 1] -= m1; z_poc[(size_t)i * DR + 2] -= m2;
+    }
+  }
+}
+
 }  // namespace dsb
 
 using namespace dsb;
@@ -780,6 +928,39 @@ int dsb_ddpm_inpaint_update(float* z_lig, float* xh_pocket, const float* xh_know
                                                                            noise_known, noise_renoise, coef, mask_atoms,
                                                                            mask_residues, (int)n_atoms, (int)n_residues, atom_nf,
                                                                            residue_nf);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dsb_ddpm_joint_update(float* z_lig, float* z_pocket, const float* eps_lig, const float* eps_pocket, const float* noise_x,
+                          const float* noise_h_lig, const float* noise_h_pocket, const float* coef, const int64_t* mask_atoms,
+                          const int64_t* mask_residues, int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int32_t atom_nf,
+                          int32_t residue_nf, void* stream) {
+  if (n_graphs <= 0) return 0;
+  if (!z_lig || !z_pocket || !eps_lig || !eps_pocket || !noise_x || !noise_h_lig || !noise_h_pocket || !coef || !mask_atoms || !mask_residues) {
+    set_error("null pointer"); return DSB_ERR_INVALID_ARGUMENT;
+  }
+  ddpm_joint_update_kernel<<<(unsigned)n_graphs, 128, 0, (cudaStream_t)stream>>>(z_lig, z_pocket, eps_lig, eps_pocket, noise_x, noise_h_lig,
+                                                                                noise_h_pocket, coef, mask_atoms, mask_residues,
+                                                                                (int)n_atoms, (int)n_residues, atom_nf, residue_nf);
+  DSB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dsb_ddpm_joint_inpaint_update(float* z_lig, float* z_pocket, const float* xh0_lig, const float* xh0_pocket,
+                                  const float* lig_fixed, const float* pocket_fixed, const float* noise_x, const float* noise_h_lig,
+                                  const float* noise_h_pocket, const float* renoise_x, const float* renoise_h_lig,
+                                  const float* renoise_h_pocket, const float* coef, const int64_t* mask_atoms,
+                                  const int64_t* mask_residues, int64_t n_atoms, int64_t n_residues, int64_t n_graphs,
+                                  int32_t atom_nf, int32_t residue_nf, void* stream) {
+  if (n_graphs <= 0) return 0;
+  if (!z_lig || !z_pocket || !xh0_lig || !xh0_pocket || !lig_fixed || !pocket_fixed || !noise_x || !noise_h_lig || !noise_h_pocket ||
+      !coef || !mask_atoms || !mask_residues || (renoise_x && (!renoise_h_lig || !renoise_h_pocket))) {
+    set_error("null pointer"); return DSB_ERR_INVALID_ARGUMENT;
+  }
+  ddpm_joint_inpaint_kernel<<<(unsigned)n_graphs, 128, 0, (cudaStream_t)stream>>>(
+      z_lig, z_pocket, xh0_lig, xh0_pocket, lig_fixed, pocket_fixed, noise_x, noise_h_lig, noise_h_pocket, renoise_x, renoise_h_lig,
+      renoise_h_pocket, coef, mask_atoms, mask_residues, (int)n_atoms, (int)n_residues, atom_nf, residue_nf);
   DSB_CUDA_OK(cudaGetLastError());
   return 0;
 }

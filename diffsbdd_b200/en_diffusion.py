@@ -157,7 +157,13 @@ class DistributionNodes:
 
 
 class EnVariationalDiffusion(nn.Module):
-    """reference en_diffusion.py:13 (constructor :18-66)."""
+    """reference en_diffusion.py:13 (constructor :18-66).
+
+    ``loop_engine``: 'auto' | 'graph' | 'eager'.  On CUDA with the native denoiser, ``sample`` and ``inpaint`` replay
+    captured CUDA graphs (denoiser + fused joint update / RePaint iteration, libdiffsbdd_b200 ``dsb_ddpm_joint_update`` /
+    ``dsb_ddpm_joint_inpaint_update``); 'eager' keeps the reference-order Python loop (same torch ops, same RNG calls)."""
+
+    loop_engine = 'auto'
 
     def __init__(self, dynamics: nn.Module, atom_nf: int, residue_nf: int, n_dims: int, size_histogram: Dict,
                  timesteps: int = 1000, parametrization='eps', noise_schedule='learned', noise_precision=1e-4,
@@ -180,6 +186,7 @@ class EnVariationalDiffusion(nn.Module):
         self.register_buffer('buffer', torch.zeros(1))
         self.size_distribution = DistributionNodes(size_histogram)
         self.vnode_idx = virtual_node_idx
+        self._joint_cache = {}                 # captured CUDA graphs of the joint samplers (see _joint_engine)
         if noise_schedule != 'learned':
             self.check_issues_norm_values()
 
@@ -338,6 +345,128 @@ class EnVariationalDiffusion(nn.Module):
         h_pocket = F.one_hot(torch.argmax(h_pocket, dim=1), self.residue_nf)
         return x_lig, h_lig, x_pocket, h_pocket
 
+    # ---- CUDA-graphed joint loops ---------------------------------------------------------------
+    def _joint_use_graph(self, device) -> bool:
+        from .dynamics import EGNNDynamics
+        if self.loop_engine == 'eager' or type(self) is not EnVariationalDiffusion:
+            return False
+        ok = isinstance(self.dynamics, EGNNDynamics) and torch.device(device).type == 'cuda'
+        if self.loop_engine == 'graph' and not ok:
+            raise RuntimeError("loop_engine='graph' needs the native EGNNDynamics on a CUDA device")
+        return ok
+
+    def _joint_tables(self, timesteps, jump_length, device):
+        """Per-step scalars (s = 0..timesteps-1, t = s+1) from the same fp32 torch ops as the eager steps:
+        t | reverse (alpha_{t|s}, sigma^2_{t|s}/alpha_{t|s}/sigma_t, sigma_{t|s} sigma_s/sigma_t) |
+        RePaint (alpha_s, sigma_s, alpha_{s+j|s}, sigma_{s+j|s}) — en_diffusion.py:503-557, :302-317, :479-501."""
+        s_int = torch.arange(timesteps, device=device).view(-1, 1)
+        t_arr, s_arr = (s_int + 1) / timesteps, s_int / timesteps
+        gamma_s, gamma_t = self.gamma(s_arr), self.gamma(t_arr)
+        sigma2_ts, sigma_ts, alpha_ts = self.sigma_and_alpha_t_given_s(gamma_t, gamma_s, s_arr)
+        sigma_s, sigma_t = self.sigma(gamma_s, s_arr), self.sigma(gamma_t, s_arr)
+        rev = [alpha_ts, sigma2_ts / alpha_ts / sigma_t, sigma_ts * sigma_s / sigma_t]
+        t_back = torch.clamp(s_int + jump_length, max=timesteps) / timesteps
+        _, sig_j, alp_j = self.sigma_and_alpha_t_given_s(self.gamma(t_back), gamma_s, s_arr)
+        inp = [self.alpha(gamma_s, s_arr), self.sigma(gamma_s, s_arr), alp_j, sig_j]
+        return t_arr.float().contiguous(), torch.cat(rev + inp, dim=1).float().contiguous()
+
+    def _joint_engine(self, z_lig, z_pocket, lig_mask, pocket_mask, n_samples, timesteps, jump_length):
+        dyn = self.dynamics
+        device = z_lig.device
+        dyn._ensure_handle(device)
+        key = (tuple(z_lig.shape), tuple(z_pocket.shape), n_samples, timesteps, jump_length, str(device))
+        st = self._joint_cache.get(key)
+        if st is not None:
+            same = torch.equal(st['lig_mask'], lig_mask) and torch.equal(st['pocket_mask'], pocket_mask)
+            if not same or st['sig'] != dyn.capture_signature():
+                st = None
+        if st is None:
+            self._joint_cache.clear()
+            t_table, coef_table = self._joint_tables(timesteps, jump_length, device)
+            nl, npk = z_lig.shape[0], z_pocket.shape[0]
+            noise = lambda: (torch.empty((nl + npk, self.n_dims), device=device), torch.empty((nl, self.atom_nf), device=device),
+                             torch.empty((npk, self.residue_nf), device=device))
+            st = dict(zl=torch.empty_like(z_lig), zp=torch.empty_like(z_pocket), n_rev=noise(), n_known=noise(), n_jump=noise(),
+                      t=torch.zeros((n_samples, 1), device=device), coef3=torch.zeros((n_samples, 3), device=device),
+                      coef4=torch.zeros((n_samples, 4), device=device), step=torch.zeros(1, dtype=torch.int64, device=device),
+                      t_table=t_table, coef_table=coef_table, lig_mask=lig_mask.clone(), pocket_mask=pocket_mask.clone(),
+                      graphs={}, sig=None, n_samples=n_samples, jump=jump_length, known=None)
+            self._joint_cache[key] = st
+        return st
+
+    def _joint_step(self, st, kind):
+        """kind: 'reverse' (sample: one joint reverse step, step -= 1) | 'inpaint' (noised known part + reverse step + blend,
+        step -= 1) | 'inpaint_jump' (the same + jump back by jump_length: step += jump_length - 1)."""
+        import ctypes as C
+        from . import _native
+        dyn, lib = self.dynamics, _native.load()
+        lm, pm, n = st['lig_mask'], st['pocket_mask'], st['n_samples']
+        NL, NP = st['zl'].shape[0], st['zp'].shape[0]
+        ptr = lambda x: x.data_ptr()
+
+        def run():
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if kind != 'reverse':                       # eager order: noised_representation draws first (en_diffusion.py:741)
+                for x in st['n_known']:
+                    x.normal_()
+            row = st['coef_table'].index_select(0, st['step'].clamp(min=0))
+            st['t'].copy_(st['t_table'].index_select(0, st['step'].clamp(min=0)).expand(n, 1))
+            st['coef3'].copy_(row[:, :3].expand(n, 3))
+            st['coef4'].copy_(row[:, 3:].expand(n, 4))
+            eps_l, eps_p = dyn(st['zl'], st['zp'], st['t'], lm, pm)
+            for x in st['n_rev']:
+                x.normal_()
+            nx, nhl, nhp = st['n_rev']
+            _native.check(lib.dsb_ddpm_joint_update(
+                ptr(st['zl']), ptr(st['zp']), ptr(eps_l), ptr(eps_p), ptr(nx), ptr(nhl), ptr(nhp), ptr(st['coef3']),
+                ptr(lm), ptr(pm), NL, NP, n, self.atom_nf, self.residue_nf, stream))
+            if kind != 'reverse':
+                kn = st['known']
+                jump = kind == 'inpaint_jump'
+                if jump:
+                    for x in st['n_jump']:
+                        x.normal_()
+                j = [ptr(x) for x in st['n_jump']] if jump else [None, None, None]
+                _native.check(lib.dsb_ddpm_joint_inpaint_update(
+                    ptr(st['zl']), ptr(st['zp']), ptr(kn['xl']), ptr(kn['xp']), ptr(kn['fl']), ptr(kn['fp']),
+                    *[ptr(x) for x in st['n_known']], *j, ptr(st['coef4']), ptr(lm), ptr(pm), NL, NP, n,
+                    self.atom_nf, self.residue_nf, stream))
+            if kind == 'inpaint_jump':
+                st['step'].add_(st['jump'] - 1)
+            else:
+                st['step'].sub_(1)
+        return run
+
+    def _joint_graph(self, st, kind, z_lig, z_pocket, first_s):
+        g = st['graphs'].get(kind)
+        if g is not None:
+            return g
+        device = z_lig.device
+        run = self._joint_step(st, kind)
+
+        def reset():
+            st['zl'].copy_(z_lig); st['zp'].copy_(z_pocket); st['step'].fill_(first_s)
+
+        rng = torch.cuda.get_rng_state(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        reset()
+        with torch.cuda.stream(side):
+            run()                                   # warm-up: allocator, plan cache, workspace
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.set_rng_state(rng, device)
+        reset()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run()
+        reset()
+        sig = self.dynamics.capture_signature()
+        if st['sig'] is not None and st['sig'] != sig:
+            st['graphs'] = {}
+        st['graphs'][kind] = g
+        st['sig'] = sig
+        return g
+
     @torch.no_grad()
     def sample(self, n_samples, num_nodes_lig, num_nodes_pocket, return_frames=1, timesteps=None, device='cpu'):
         """en_diffusion.py:581-651: unconditional joint sampling of ligand and pocket."""
@@ -350,14 +479,32 @@ class EnVariationalDiffusion(nn.Module):
         self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :self.n_dims], z_pocket[:, :self.n_dims])), combined_mask)
         out_lig = torch.zeros((return_frames,) + z_lig.size(), device=z_lig.device)
         out_pocket = torch.zeros((return_frames,) + z_pocket.size(), device=z_pocket.device)
-        for s in reversed(range(0, timesteps)):
-            s_arr = torch.full((n_samples, 1), fill_value=s, device=z_lig.device)
-            t_arr = (s_arr + 1) / timesteps
-            s_arr = s_arr / timesteps
-            z_lig, z_pocket = self.sample_p_zs_given_zt(s_arr, t_arr, z_lig, z_pocket, lig_mask, pocket_mask)
-            if (s * return_frames) % timesteps == 0:
-                idx = (s * return_frames) // timesteps
-                out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, z_pocket)
+        if self._joint_use_graph(z_lig.device):
+            dyn = self.dynamics
+            st = self._joint_engine(z_lig, z_pocket, lig_mask, pocket_mask, n_samples, timesteps, 1)
+            prev_defer, dyn.defer_status_check = dyn.defer_status_check, True
+            try:
+                g = self._joint_graph(st, 'reverse', z_lig, z_pocket, timesteps - 1)
+                st['zl'].copy_(z_lig); st['zp'].copy_(z_pocket); st['step'].fill_(timesteps - 1)
+                for s in reversed(range(0, timesteps)):
+                    g.replay()
+                    if (s * return_frames) % timesteps == 0:
+                        idx = (s * return_frames) // timesteps
+                        out_lig[idx], out_pocket[idx] = self.unnormalize_z(st['zl'], st['zp'])
+            finally:
+                dyn.defer_status_check = prev_defer
+            dyn.check_status()
+            z_lig, z_pocket = st['zl'].clone(), st['zp'].clone()
+            self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :self.n_dims], z_pocket[:, :self.n_dims])), combined_mask)
+        else:
+            for s in reversed(range(0, timesteps)):
+                s_arr = torch.full((n_samples, 1), fill_value=s, device=z_lig.device)
+                t_arr = (s_arr + 1) / timesteps
+                s_arr = s_arr / timesteps
+                z_lig, z_pocket = self.sample_p_zs_given_zt(s_arr, t_arr, z_lig, z_pocket, lig_mask, pocket_mask)
+                if (s * return_frames) % timesteps == 0:
+                    idx = (s * return_frames) // timesteps
+                    out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, z_pocket)
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(z_lig, z_pocket, lig_mask, pocket_mask, n_samples)
         self.assert_mean_zero_with_mask(torch.cat((x_lig, x_pocket), dim=0), combined_mask)
         if return_frames == 1:
@@ -424,36 +571,75 @@ class EnVariationalDiffusion(nn.Module):
 
         schedule = self.get_repaint_schedule(resamplings, jump_length, timesteps)
         s = timesteps - 1
-        for i, n_denoise in enumerate(schedule):
-            for j in range(n_denoise):
-                s_array = torch.full((n_samples, 1), fill_value=s, device=z_lig.device)
-                t_array = (s_array + 1) / timesteps
-                s_array = s_array / timesteps
-                gamma_s = self.inflate_batch_array(self.gamma(s_array), ligand['x'])
-                # known nodes: forward-noised data; unknown nodes: one reverse step (en_diffusion.py:741-749)
-                zk_lig, zk_pocket, _, _ = self.noised_representation(xh0_lig, xh0_pocket, lmask, pmask, gamma_s)
-                zu_lig, zu_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, z_pocket, lmask, pmask)
-                # align the COM of the noised known part with the denoised one (en_diffusion.py:751-772)
-                shift = self._fixed_com(zu_lig[:, :nd], zu_pocket[:, :nd], lsel, psel, lmask, pmask) - \
-                    self._fixed_com(zk_lig[:, :nd], zk_pocket[:, :nd], lsel, psel, lmask, pmask)
-                zk_lig[:, :nd] = zk_lig[:, :nd] + shift[lmask]
-                zk_pocket[:, :nd] = zk_pocket[:, :nd] + shift[pmask]
-                z_lig = zk_lig * lig_fixed + zu_lig * (1 - lig_fixed)
-                z_pocket = zk_pocket * pocket_fixed + zu_pocket * (1 - pocket_fixed)
-                self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :nd], z_pocket[:, :nd]), dim=0), combined_mask)
-
-                if (n_denoise > jump_length or i == len(schedule) - 1) and (s * return_frames) % timesteps == 0:
-                    idx = (s * return_frames) // timesteps
-                    out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, z_pocket)
-
-                if j == n_denoise - 1 and i < len(schedule) - 1:      # jump back jump_length steps (en_diffusion.py:790-807)
-                    t = s + jump_length
-                    t_back = torch.full((n_samples, 1), fill_value=t, device=z_lig.device) / timesteps
+        if self._joint_use_graph(z_lig.device):
+            dyn = self.dynamics
+            st = self._joint_engine(z_lig, z_pocket, lmask, pmask, n_samples, timesteps, jump_length)
+            if st['known'] is None:       # static buffers the captured RePaint iteration reads
+                st['known'] = dict(xl=torch.empty_like(xh0_lig), xp=torch.empty_like(xh0_pocket),
+                                   fl=torch.empty(len(lmask), device=z_lig.device), fp=torch.empty(len(pmask), device=z_lig.device))
+            kn = st['known']
+            kn['xl'].copy_(xh0_lig); kn['xp'].copy_(xh0_pocket); kn['fl'].copy_(lig_fixed.view(-1)); kn['fp'].copy_(pocket_fixed.view(-1))
+            prev_defer, dyn.defer_status_check = dyn.defer_status_check, True
+            try:
+                g_it = self._joint_graph(st, 'inpaint', z_lig, z_pocket, s)
+                g_jump = self._joint_graph(st, 'inpaint_jump', z_lig, z_pocket, s) if len(schedule) > 1 else None
+                st['zl'].copy_(z_lig); st['zp'].copy_(z_pocket); st['step'].fill_(s)
+                for i, n_denoise in enumerate(schedule):
+                    for j in range(n_denoise):
+                        jump = j == n_denoise - 1 and i < len(schedule) - 1
+                        frame = (n_denoise > jump_length or i == len(schedule) - 1) and (s * return_frames) % timesteps == 0
+                        # a frame is taken after the blend and BEFORE the jump back (en_diffusion.py:777-788): in that case the
+                        # jump runs as eager torch ops on the static state instead of inside the fused kernel
+                        (g_jump if (jump and not frame) else g_it).replay()
+                        if frame:
+                            idx = (s * return_frames) // timesteps
+                            out_lig[idx], out_pocket[idx] = self.unnormalize_z(st['zl'], st['zp'])
+                        if jump:
+                            if frame:
+                                s_arr = torch.full((n_samples, 1), fill_value=s, device=z_lig.device) / timesteps
+                                t_back = torch.full((n_samples, 1), fill_value=s + jump_length, device=z_lig.device) / timesteps
+                                zl, zp = self.sample_p_zt_given_zs(
+                                    st['zl'], st['zp'], lmask, pmask, self.inflate_batch_array(self.gamma(t_back), ligand['x']),
+                                    self.inflate_batch_array(self.gamma(s_arr), ligand['x']))
+                                st['zl'].copy_(zl); st['zp'].copy_(zp); st['step'].add_(jump_length)
+                            s = s + jump_length
+                        s -= 1
+            finally:
+                dyn.defer_status_check = prev_defer
+            dyn.check_status()
+            z_lig, z_pocket = st['zl'].clone(), st['zp'].clone()
+            self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :nd], z_pocket[:, :nd]), dim=0), combined_mask)
+        else:
+            for i, n_denoise in enumerate(schedule):
+                for j in range(n_denoise):
+                    s_array = torch.full((n_samples, 1), fill_value=s, device=z_lig.device)
+                    t_array = (s_array + 1) / timesteps
+                    s_array = s_array / timesteps
                     gamma_s = self.inflate_batch_array(self.gamma(s_array), ligand['x'])
-                    gamma_t = self.inflate_batch_array(self.gamma(t_back), ligand['x'])
-                    z_lig, z_pocket = self.sample_p_zt_given_zs(z_lig, z_pocket, lmask, pmask, gamma_t, gamma_s)
-                    s = t
-                s -= 1
+                    # known nodes: forward-noised data; unknown nodes: one reverse step (en_diffusion.py:741-749)
+                    zk_lig, zk_pocket, _, _ = self.noised_representation(xh0_lig, xh0_pocket, lmask, pmask, gamma_s)
+                    zu_lig, zu_pocket = self.sample_p_zs_given_zt(s_array, t_array, z_lig, z_pocket, lmask, pmask)
+                    # align the COM of the noised known part with the denoised one (en_diffusion.py:751-772)
+                    shift = self._fixed_com(zu_lig[:, :nd], zu_pocket[:, :nd], lsel, psel, lmask, pmask) - \
+                        self._fixed_com(zk_lig[:, :nd], zk_pocket[:, :nd], lsel, psel, lmask, pmask)
+                    zk_lig[:, :nd] = zk_lig[:, :nd] + shift[lmask]
+                    zk_pocket[:, :nd] = zk_pocket[:, :nd] + shift[pmask]
+                    z_lig = zk_lig * lig_fixed + zu_lig * (1 - lig_fixed)
+                    z_pocket = zk_pocket * pocket_fixed + zu_pocket * (1 - pocket_fixed)
+                    self.assert_mean_zero_with_mask(torch.cat((z_lig[:, :nd], z_pocket[:, :nd]), dim=0), combined_mask)
+
+                    if (n_denoise > jump_length or i == len(schedule) - 1) and (s * return_frames) % timesteps == 0:
+                        idx = (s * return_frames) // timesteps
+                        out_lig[idx], out_pocket[idx] = self.unnormalize_z(z_lig, z_pocket)
+
+                    if j == n_denoise - 1 and i < len(schedule) - 1:      # jump back jump_length steps (en_diffusion.py:790-807)
+                        t = s + jump_length
+                        t_back = torch.full((n_samples, 1), fill_value=t, device=z_lig.device) / timesteps
+                        gamma_s = self.inflate_batch_array(self.gamma(s_array), ligand['x'])
+                        gamma_t = self.inflate_batch_array(self.gamma(t_back), ligand['x'])
+                        z_lig, z_pocket = self.sample_p_zt_given_zs(z_lig, z_pocket, lmask, pmask, gamma_t, gamma_s)
+                        s = t
+                    s -= 1
 
         x_lig, h_lig, x_pocket, h_pocket = self.sample_p_xh_given_z0(z_lig, z_pocket, lmask, pmask, n_samples)
         self.assert_mean_zero_with_mask(torch.cat((x_lig, x_pocket), dim=0), combined_mask)

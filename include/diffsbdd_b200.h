@@ -176,6 +176,28 @@ int dsb_ddpm_inpaint_update(float* z_lig, float* xh_pocket, const float* xh_know
                             int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int32_t atom_nf,
                             int32_t residue_nf, void* stream);
 
+/* ---- joint model (EnVariationalDiffusion, update_pocket_coords = 1): the same two fusions for ligand AND pocket.
+ * noise_x is ONE tensor [n_atoms + n_residues, 3] (ligand rows first) as sample_center_gravity_zero_gaussian_batch draws it
+ * (en_diffusion.py:559-578); its per-graph mean over ligand+pocket nodes is removed inside the kernel (:940-944).
+ * dsb_ddpm_joint_update  = tail of EnVariationalDiffusion.sample_p_zs_given_zt (en_diffusion.py:540-557):
+ *   z' = z/alpha_ts - coef1 * eps_hat + sigma * eps ; joint COM of z'.x removed.  coef [n_graphs, 3] as dsb_ddpm_ligand_update.
+ * dsb_ddpm_joint_inpaint_update = one RePaint iteration of EnVariationalDiffusion.inpaint after that step (:741-807):
+ *   z_known = alpha_s xh0 + sigma_s eps ; COM of the fixed nodes aligned noised -> denoised ; blend by lig_fixed / pocket_fixed ;
+ *   if renoise_x != NULL: jump back z = alpha_{t|s} z + sigma_{t|s} eps' with the joint COM removed (sample_p_zt_given_zs).
+ *   coef [n_graphs, 4] = (alpha_s, sigma_s, alpha_{t|s}, sigma_{t|s}); xh0_* = known data, normalised and centred as :707-717. */
+int dsb_ddpm_joint_update(float* z_lig, float* z_pocket, const float* eps_lig, const float* eps_pocket,
+                          const float* noise_x, const float* noise_h_lig, const float* noise_h_pocket,
+                          const float* coef, const int64_t* mask_atoms, const int64_t* mask_residues,
+                          int64_t n_atoms, int64_t n_residues, int64_t n_graphs, int32_t atom_nf,
+                          int32_t residue_nf, void* stream);
+int dsb_ddpm_joint_inpaint_update(float* z_lig, float* z_pocket, const float* xh0_lig, const float* xh0_pocket,
+                                  const float* lig_fixed, const float* pocket_fixed, const float* noise_x,
+                                  const float* noise_h_lig, const float* noise_h_pocket, const float* renoise_x,
+                                  const float* renoise_h_lig, const float* renoise_h_pocket, const float* coef,
+                                  const int64_t* mask_atoms, const int64_t* mask_residues, int64_t n_atoms,
+                                  int64_t n_residues, int64_t n_graphs, int32_t atom_nf, int32_t residue_nf,
+                                  void* stream);
+
 const char* dsb_last_error(void);
 const char* dsb_version(void);
 

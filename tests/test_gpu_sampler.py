@@ -360,3 +360,120 @@ def test_joint_repaint_inpaint_denoiser_calls_match_oracle():
     assert torch.all(out[0][:, 3:].sum(1) == 1) and torch.all(out[1][:, 3:].sum(1) == 1)
     com = scatter_mean(torch.cat((out[0][:, :3], out[1][:, :3])), torch.cat((out[2], out[3])))
     assert com.abs().max() < 5e-2 * max(1.0, float(out[1][:, :3].abs().max()))
+
+
+def _joint_ref_noise(nx, lm, pm):
+    """COM-free position noise as sample_center_gravity_zero_gaussian_batch builds it (en_diffusion.py:940-944)."""
+    cm = torch.cat((lm, pm))
+    return nx - scatter_mean(nx, cm)[cm]
+
+
+def test_fused_joint_kernels_match_torch_ops():
+    """dsb_ddpm_joint_update / dsb_ddpm_joint_inpaint_update against the torch ops of the eager joint sampler
+    (en_diffusion.py:503-557, :741-807), ragged graphs, partially fixed pocket, with and without the jump back."""
+    g = torch.Generator().manual_seed(3)
+    n_lig, n_poc = [5, 1, 8], [9, 6, 4]
+    A, R, B = 10, 10, 3
+    lm = torch.repeat_interleave(torch.arange(B), torch.tensor(n_lig)).cuda()
+    pm = torch.repeat_interleave(torch.arange(B), torch.tensor(n_poc)).cuda()
+    cm = torch.cat((lm, pm))
+    NL, NP = sum(n_lig), sum(n_poc)
+    rnd = lambda *shape: torch.randn(shape, generator=g).cuda()
+    zl, zp, el, ep = rnd(NL, 3 + A), rnd(NP, 3 + R), rnd(NL, 3 + A), rnd(NP, 3 + R)
+    nx, nhl, nhp = rnd(NL + NP, 3), rnd(NL, A), rnd(NP, R)
+    coef3 = (torch.rand((B, 3), generator=g) + 0.5).cuda()
+    lib = _native.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: t.data_ptr()
+
+    ex = _joint_ref_noise(nx, lm, pm)
+    eps_l, eps_p = torch.cat((ex[:NL], nhl), 1), torch.cat((ex[NL:], nhp), 1)
+    wl = zl / coef3[lm, 0:1] - coef3[lm, 1:2] * el + coef3[lm, 2:3] * eps_l
+    wp = zp / coef3[pm, 0:1] - coef3[pm, 1:2] * ep + coef3[pm, 2:3] * eps_p
+    mean = scatter_mean(torch.cat((wl[:, :3], wp[:, :3])), cm)
+    wl[:, :3] -= mean[lm]; wp[:, :3] -= mean[pm]
+    a, b = zl.clone(), zp.clone()
+    _native.check(lib.dsb_ddpm_joint_update(P(a), P(b), P(el), P(ep), P(nx), P(nhl), P(nhp), P(coef3), P(lm), P(pm), NL, NP, B, A, R, stream))
+    torch.cuda.synchronize()
+    assert torch.allclose(a, wl, atol=3e-6, rtol=1e-5) and torch.allclose(b, wp, atol=3e-6, rtol=1e-5)
+
+    x0l, x0p = rnd(NL, 3 + A), rnd(NP, 3 + R)
+    fl = (torch.rand(NL, generator=g) < 0.4).float().cuda()
+    fp = (torch.rand(NP, generator=g) < 0.7).float().cuda()
+    fl[0] = 1
+    coef4 = (torch.rand((B, 4), generator=g) * 0.8 + 0.1).cuda()
+    n3 = (rnd(NL + NP, 3), rnd(NL, A), rnd(NP, R))
+    for jump in (False, True):
+        zkl = coef4[lm, 0:1] * x0l + coef4[lm, 1:2] * eps_l
+        zkp = coef4[pm, 0:1] * x0p + coef4[pm, 1:2] * eps_p
+        sel_l, sel_p = fl.bool(), fp.bool()
+        idx = torch.cat((lm[sel_l], pm[sel_p]))
+        com_u = scatter_mean(torch.cat((zl[sel_l][:, :3], zp[sel_p][:, :3])), idx, dim_size=B)
+        com_k = scatter_mean(torch.cat((zkl[sel_l][:, :3], zkp[sel_p][:, :3])), idx, dim_size=B)
+        shift = com_u - com_k
+        zkl[:, :3] += shift[lm]; zkp[:, :3] += shift[pm]
+        wl = zkl * fl[:, None] + zl * (1 - fl[:, None])
+        wp = zkp * fp[:, None] + zp * (1 - fp[:, None])
+        if jump:
+            e3 = _joint_ref_noise(n3[0], lm, pm)
+            wl = coef4[lm, 2:3] * wl + coef4[lm, 3:4] * torch.cat((e3[:NL], n3[1]), 1)
+            wp = coef4[pm, 2:3] * wp + coef4[pm, 3:4] * torch.cat((e3[NL:], n3[2]), 1)
+            mean = scatter_mean(torch.cat((wl[:, :3], wp[:, :3])), cm)
+            wl[:, :3] -= mean[lm]; wp[:, :3] -= mean[pm]
+        a, b = zl.clone(), zp.clone()
+        j = [P(x) for x in n3] if jump else [None, None, None]
+        _native.check(lib.dsb_ddpm_joint_inpaint_update(P(a), P(b), P(x0l), P(x0p), P(fl), P(fp), P(nx), P(nhl), P(nhp), *j,
+                                                        P(coef4), P(lm), P(pm), NL, NP, B, A, R, stream))
+        torch.cuda.synchronize()
+        assert torch.allclose(a, wl, atol=3e-6, rtol=1e-5), float((a - wl).abs().max())
+        assert torch.allclose(b, wp, atol=3e-6, rtol=1e-5), float((b - wp).abs().max())
+
+
+def _joint_pair(T):
+    eager, graph = _build_joint(T, 'cuda', native=True), _build_joint(T, 'cuda', native=True)
+    eager.loop_engine, graph.loop_engine = 'eager', 'graph'
+    return eager, graph
+
+
+def test_joint_graph_sample_matches_eager_same_seed():
+    """EnVariationalDiffusion.sample: captured joint reverse step (native denoiser + dsb_ddpm_joint_update) vs the
+    reference-order eager loop with the same CUDA seed (three randn draws per step in the same order)."""
+    T = 4
+    eager, graph = _joint_pair(T)
+    n_lig, n_poc = torch.tensor([6, 4]).cuda(), torch.tensor([14, 11]).cuda()
+    outs = []
+    for ddpm in (eager, graph):
+        torch.manual_seed(31)
+        outs.append(ddpm.sample(2, n_lig, n_poc, device='cuda'))
+    a, b = outs
+    assert graph._joint_cache and 'reverse' in next(iter(graph._joint_cache.values()))['graphs']
+    scale = max(1.0, float(a[1][:, :3].abs().max()))
+    assert torch.allclose(a[0][:, :3], b[0][:, :3], atol=2e-3 * scale), float((a[0] - b[0]).abs().max())
+    assert torch.allclose(a[1][:, :3], b[1][:, :3], atol=2e-3 * scale), float((a[1] - b[1]).abs().max())
+    com = scatter_mean(torch.cat((b[0][:, :3], b[1][:, :3])), torch.cat((b[2], b[3])))
+    assert com.abs().max() < 5e-2 * scale
+
+
+@pytest.mark.parametrize('case', ['joint_inpaint_T6_r2_j2', 'joint_inpaint_T4_r3_partial_pocket', 'joint_inpaint_T8_sub4_frames2'])
+def test_joint_graph_inpaint_matches_eager_same_seed(case):
+    """EnVariationalDiffusion.inpaint (RePaint schedule with jumps, partially free pocket, frames): captured iteration graphs vs
+    the eager loop with the same seed.  The end point of a joint trajectory is sensitive, so the comparison uses a
+    loose tolerance; the fused kernels themselves are checked exactly in test_fused_joint_kernels_match_torch_ops."""
+    from ddpm_cases import JOINT_CASES, make_pocket_fixed
+    spec = JOINT_CASES[case]
+    eager, graph = _joint_pair(spec['T'])
+    outs = []
+    for ddpm in (eager, graph):
+        lig, fixed = make_ligand(spec['n_lig'], spec['n_fixed'], device='cuda')
+        pocket = make_pocket('cuda')
+        pfix = make_pocket_fixed(spec, pocket).cuda()
+        torch.manual_seed(spec['seed'])
+        outs.append(ddpm.inpaint(lig, pocket, fixed, pfix, resamplings=spec['resamplings'], jump_length=spec['jump_length'],
+                                 return_frames=spec['frames'], timesteps=spec['timesteps']))
+    a, b = outs
+    st = next(iter(graph._joint_cache.values()))
+    assert 'inpaint' in st['graphs']
+    assert a[0].shape == b[0].shape and all(torch.isfinite(o).all() for o in b[:2])
+    scale = max(1.0, float(a[1][..., :3].abs().max()))
+    assert torch.allclose(a[0][..., :3], b[0][..., :3], atol=2e-2 * scale), float((a[0] - b[0]).abs().max())
+    assert torch.allclose(a[1][..., :3], b[1][..., :3], atol=2e-2 * scale), float((a[1] - b[1]).abs().max())
