@@ -602,6 +602,7 @@ template <int H>
 struct EdgeExtra {            // shared memory after Control
   float vec[2][3 * H];     // per MLP: wr, wr0, b2   (the edge-type table tb stays in global/L1)
   float wa[H];                // attention weight (GCL) or w3 (coord)
+  float gate4[EPI_WARPS][32]; // GCL pass 2: attention gates of the warp's 32 rows (read back per 4-row chunk)
   float d2[NSCAL][TM], d0[NSCAL][TM];       // per-edge scalars: NSCAL sets so the scalar warps run a full tile ahead of the
   int row[NSCAL][TM], col[NSCAL][TM], type[NSCAL][TM];   // producers while the epilogue still reads the set of the tile before
   union {
@@ -665,7 +666,7 @@ __device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra<H>* 
 // are independent units that add into the same receiver sums: units, not edge tiles, are dealt round-robin to the CTAs (610 edge
 // tiles on 148 CTAs would leave 21 % of the machine idle in the last wave; 1220 units leave 9 %).  The j-th unit of a CTA uses
 // scalar set j % NSCAL and accumulator j & 1.
-template <bool COORD, bool F16, int H>
+template <bool COORD, bool F16, int H, bool TB>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
   using G = Geo<H>;
   constexpr int TN = H;
@@ -678,7 +679,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
   constexpr int halves = H / TKC;           // 32-k production steps per unit
   constexpr int HPC = F16 ? 2 : 1;             // production steps per pipeline chunk (stage)
   constexpr int chunks = halves / HPC;
-  const bool has_tb = a.tb[0] != nullptr;
 
   pdl_trigger();
   for (int i = threadIdx.x; i < H; i += EDGE_THREADS) {
@@ -758,38 +758,42 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         tmem_wait_st();
         const float gate = myrow >= 0 ? (has_att ? sigmoid_f(s + ba) : 1.0f) : 0.f;    // pad rows share a chunk with real rows: weight 0
         // Receiver segments start at multiples of kRowChunk rows (virtual edge order), so every chunk of 4 rows belongs to one
-        // receiver (or is padding): no segment search.  crow[k] = receiver of chunk k of this warp's 32 rows.
-        static_assert(kRowChunk == 4, "chunk sums below assume 4-row chunks");
+        // receiver (or is padding): no segment search.  Pass 2 works per 32-column block: the activated messages go row-wise
+        // (STS.128, unscaled) into the per-warp buffer; lane (k = lane / 4, g = lane % 4) then owns chunk k x columns
+        // {4g..4g+3, 16+4g..16+4g+3}: 8 LDS.128 (4 rows x 2 pieces, conflict-free: the quarter-warp's rows are 4 x 36 words
+        // apart), the gate-weighted 4-row sums as 16 FFMA2, two 16-byte RED (red.global.add.v4.f32) into the receiver's row.
         // A chunk of padding only (tile tail) has gate 0 on all rows: its sums are exactly 0 and are added to row 0.
-        int crow[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) crow[k] = max(ex->row[par][warp * 32 + 4 * k], 0);
-        const f32x2 gp = pk2(gate, gate);
-        // pass 2: e = m * gate -> row-wise STS.128 into the per-warp buffer -> each lane reads its column (32 independent
-        // LDS), sums 4-row chunks -> one RED per (chunk, column); REDs to the same receiver meet in L2
+        static_assert(kRowChunk == 4, "chunk sums below assume 4-row chunks");
+        float* G4 = ex->gate4[warp];
+        G4[lane] = gate;
+        __syncwarp();
+        const int ck = lane >> 2, cg = lane & 3;
+        const float4 gq = *reinterpret_cast<const float4*>(G4 + 4 * ck);         // gates of the chunk's four rows
+        const f32x2 g0 = pk2(gq.x, gq.x), g1 = pk2(gq.y, gq.y), g2 = pk2(gq.z, gq.z), g3 = pk2(gq.w, gq.w);
+        const int crow = max(ex->row[par][warp * 32 + 4 * ck], 0);
+        float* const dst0 = a.agg + (size_t)crow * H + 4 * cg;
+        const float* const tp = T + (4 * ck) * EPI_T_STRIDE + 4 * cg;
 #pragma unroll kE2Unroll
         for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
           float v[32];
           tmem_ld32(taddr + cb * 32, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-          {
-            float4 o;
-            upk2(mul2(pk2(v[4 * q], v[4 * q + 1]), gp), o.x, o.y);
-            upk2(mul2(pk2(v[4 * q + 2], v[4 * q + 3]), gp), o.z, o.w);
-            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) = o;
-          }
+            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
           if (!(edbg & 1024)) {
-            const float* tp = T + lane;
-            float* dst = a.agg + cb * 32 + lane;
-            float t[32];
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) t[rr] = tp[rr * EPI_T_STRIDE];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float sum = (t[4 * k] + t[4 * k + 1]) + (t[4 * k + 2] + t[4 * k + 3]);
-              atomicAdd(dst + (size_t)crow[k] * H, sum);
+            for (int hp = 0; hp < 2; ++hp) {
+              const float4 x0 = *reinterpret_cast<const float4*>(tp + 16 * hp);
+              const float4 x1 = *reinterpret_cast<const float4*>(tp + 16 * hp + EPI_T_STRIDE);
+              const float4 x2 = *reinterpret_cast<const float4*>(tp + 16 * hp + 2 * EPI_T_STRIDE);
+              const float4 x3 = *reinterpret_cast<const float4*>(tp + 16 * hp + 3 * EPI_T_STRIDE);
+              // ((g0 x0 + g1 x1) + (g2 x2 + g3 x3)): two independent chains per pair
+              const f32x2 s01 = add2(fma2(g1, pk2(x1.x, x1.y), mul2(g0, pk2(x0.x, x0.y))), fma2(g3, pk2(x3.x, x3.y), mul2(g2, pk2(x2.x, x2.y))));
+              const f32x2 s23 = add2(fma2(g1, pk2(x1.z, x1.w), mul2(g0, pk2(x0.z, x0.w))), fma2(g3, pk2(x3.z, x3.w), mul2(g2, pk2(x2.z, x2.w))));
+              float o0, o1, o2, o3;
+              upk2(s01, o0, o1); upk2(s23, o2, o3);
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst0 + cb * 32 + 16 * hp), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
             }
           }
           __syncwarp();
@@ -857,36 +861,42 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     const int dbg = tc_debug();
     const bool pprof = !COORD && (dbg & 512) && ptid == 0;
     uint32_t gc = 0;
+    const int r0 = 16 * pw + 4 * sr;           // first of this thread's four tile rows
+    // Everything that does not change from chunk to chunk is computed once: the swizzled byte offsets of the thread's four
+    // operand rows (the second 32-k half of a 3xFP16 chunk sits 64 bytes further in the swizzled row: offset ^ 64), and, per
+    // unit, the five 64-bit row pointers of the gathers.  With the chunk loop unrolled every gather is `pointer + immediate`
+    // and every operand store `stage + register offset` (the address arithmetic was ~40 % of the loop's instructions).
+    uint32_t so[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) so[i] = F16 ? sw128_offset(r0 + i, pc >> 1) + (uint32_t)(pc & 1) * 8u : sw128_offset(r0 + i, pc);
     float pd2[4], pd0[4];
-    const float* const Pt = a.P + 4 * pc;      // this thread's 16-byte piece of a P row; rows/blocks are added per load
-    int prow = 0, pcol[4] = {0, 0, 0, 0}, pty[4] = {0, 0, 0, 0};
-    int moff = 0;                              // column offset of the unit's MLP inside the receiver / sender blocks
-    const int soff = nm * H;                // sender block follows the nm receiver blocks
+    const float* const Pt = a.P + 4 * pc;      // this thread's 16-byte piece of a P row
+    const float* pr = Pt;                      // receiver row of the thread's 4-row chunk (this unit's MLP block)
+    const float* ps[4] = {Pt, Pt, Pt, Pt};     // the four sender rows
+    int pty[4] = {0, 0, 0, 0};
+    const int soff = nm * H;                   // sender block follows the nm receiver blocks
     float4 ga, gb[4], ga2, gb2[4];
-    auto setup_unit = [&](int j) {             // row indices and scalars of unit j; returns its MLP index
+    auto setup_unit = [&](int j) {             // row pointers and scalars of unit j; returns its MLP index
       int m;
       unit_tile(j, m);
       const int par = j % NSCAL;
       mbar_wait(&ctl->scal_full[par], (uint32_t)(j / NSCAL) & 1u);
-      const int r0 = 16 * pw + 4 * sr;
-      prow = max(ex->row[par][r0], 0);
-      moff = m * H;
+      const int moff = m * H;                  // column offset of the unit's MLP inside the receiver / sender blocks
+      pr = Pt + (size_t)max(ex->row[par][r0], 0) * a.ldp + moff;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        pcol[i] = ex->col[par][r0 + i];
+        ps[i] = Pt + (size_t)ex->col[par][r0 + i] * a.ldp + (soff + moff);
         pd2[i] = ex->d2[par][r0 + i]; pd0[i] = ex->d0[par][r0 + i];
-        if (has_tb) pty[i] = ex->type[par][r0 + i] * H;
+        if (TB) pty[i] = ex->type[par][r0 + i] * H;
       }
       return m;
     };
-    auto recv_ptr = [&](int hf) { return Pt + (size_t)prow * a.ldp + (moff + hf * TKC); };
-    auto send_ptr = [&](int i, int hf) { return Pt + (size_t)pcol[i] * a.ldp + (soff + moff + hf * TKC); };
     const bool no_gather = (dbg & 64) != 0;        // instrumented builds only: operands from registers instead of L2
     auto ld4 = [&](const float* p) { return no_gather ? make_float4(0.1f, -0.2f, 0.3f, 0.05f) : *reinterpret_cast<const float4*>(p); };
     auto issue = [&](int hf, float4& xa, float4 (&xb)[4]) {
-      xa = ld4(recv_ptr(hf));
+      xa = ld4(pr + hf * TKC);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xb[i] = ld4(send_ptr(i, hf));
+      for (int i = 0; i < 4; ++i) xb[i] = ld4(ps[i] + hf * TKC);
     };
     long long t0 = 0, t1 = 0, t2 = 0, acc_wait = 0, acc_comp = 0, acc_fence = 0;
     const long long pp0 = pprof ? tc_clock() : 0;
@@ -894,8 +904,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     issue(0, ga, gb);
     for (int j = 0; j < n_my; ++j) {
       const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H;
-      const float* tbm = has_tb ? a.tb[m] + 4 * pc : nullptr;
-#pragma unroll 1
+      const float* tbm = TB ? a.tb[m] + 4 * pc : nullptr;
+#pragma unroll
       for (int kc = 0; kc < chunks; ++kc) {
         const int s = gc & 1;
         char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
@@ -911,21 +921,19 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
             const f32x2 a01 = pk2(ga.x, ga.y), a23 = pk2(ga.z, ga.w);
-            if (!last_half) ga = ld4(recv_ptr(hf + 1));        // (i)
+            if (!last_half) ga = ld4(pr + (hf + 1) * TKC);        // (i)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const f32x2 d2p = pk2(pd2[i], pd2[i]), d0p = pk2(pd0[i], pd0[i]);
               f32x2 u01 = fma2(d0p, pk2(r04.x, r04.y), fma2(d2p, pk2(r4.x, r4.y), add2(a01, pk2(gb[i].x, gb[i].y))));
               f32x2 u23 = fma2(d0p, pk2(r04.z, r04.w), fma2(d2p, pk2(r4.z, r4.w), add2(a23, pk2(gb[i].z, gb[i].w))));
-              if (!last_half) gb[i] = ld4(send_ptr(i, hf + 1));   // (i): registers of row i are free
-              if (has_tb) {
+              if (!last_half) gb[i] = ld4(ps[i] + (hf + 1) * TKC);   // (i): registers of row i are free
+              if (TB) {
                 const float4 t4 = *reinterpret_cast<const float4*>(tbm + pty[i] + hf * TKC);
                 u01 = add2(u01, pk2(t4.x, t4.y)); u23 = add2(u23, pk2(t4.z, t4.w));
               }
               if (!(dbg & 128)) { u01 = silu2(u01); u23 = silu2(u23); }      // 128: instrumented builds only
-              float4 v;
-              upk2(u01, v.x, v.y); upk2(u23, v.z, v.w);
-              store_piece<F16>(st, 16 * pw + 4 * sr + i, hf, pc, v);
+              store_pair<F16>(st + (F16 && (hf & 1) ? (so[i] ^ 64u) : so[i]), u01, u23);
             }
           }
         }
@@ -1015,10 +1023,14 @@ int configure_tc_kernels(int H) {
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
     return 0;
   });
 }
@@ -1077,8 +1089,9 @@ int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
   a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg; a.status = status;
   return dispatch_width(d->cfg.hidden_nf, [&]<int W>() -> int {
-    DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<false, true, W> : tc_edge_kernel<false, false, W>, d->num_sms, EDGE_THREADS,
-                         edge_smem_bytes<W>(), s, a));
+    auto kern = w.tb ? (f16 ? tc_edge_kernel<false, true, W, true> : tc_edge_kernel<false, false, W, true>)
+                     : (f16 ? tc_edge_kernel<false, true, W, false> : tc_edge_kernel<false, false, W, false>);
+    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W>(), s, a));
     return 0;
   });
 }
@@ -1099,8 +1112,9 @@ int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace&
   a.wa = w.w3; a.ba = nullptr;
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg; a.status = status;
   return dispatch_width(c.hidden_nf, [&]<int W>() -> int {
-    DSB_CUDA_OK(launch_k(f16 ? tc_edge_kernel<true, true, W> : tc_edge_kernel<true, false, W>, d->num_sms, EDGE_THREADS,
-                         edge_smem_bytes<W>(), s, a));
+    auto kern = w.tb[0] ? (f16 ? tc_edge_kernel<true, true, W, true> : tc_edge_kernel<true, false, W, true>)
+                        : (f16 ? tc_edge_kernel<true, true, W, false> : tc_edge_kernel<true, false, W, false>);
+    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W>(), s, a));
     return 0;
   });
 }

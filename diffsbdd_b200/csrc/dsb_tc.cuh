@@ -247,6 +247,31 @@ __device__ __forceinline__ void store_piece(char* st, int row, int half, int p, 
   }
 }
 
+// Same split as store_piece, for a row piece already held as two packed pairs and a precomputed destination address
+// (stage base + swizzled offset of the row piece): the residual is one packed subtraction.
+__device__ __forceinline__ f32x2 sub2_(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+template <bool F16>
+__device__ __forceinline__ void store_pair(char* dst, f32x2 u01, f32x2 u23) {
+  float x0, x1, x2, x3;
+  upk2(u01, x0, x1); upk2(u23, x2, x3);
+  if constexpr (F16) {
+    const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    float l0, l1, l2, l3;
+    upk2(sub2_(u01, pk2(f0.x, f0.y)), l0, l1); upk2(sub2_(u23, pk2(f1.x, f1.y)), l2, l3);
+    const __half2 q0 = __floats2half2_rn(l0, l1), q1 = __floats2half2_rn(l2, l3);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lv.x = *reinterpret_cast<const uint32_t*>(&q0); lv.y = *reinterpret_cast<const uint32_t*>(&q1);
+    *reinterpret_cast<uint2*>(dst) = hv;
+    *reinterpret_cast<uint2*>(dst + A_CHUNK_BYTES) = lv;
+  } else {
+    const float4 h = make_float4(tf32_hi(x0), tf32_hi(x1), tf32_hi(x2), tf32_hi(x3));
+    *reinterpret_cast<float4*>(dst) = h;
+    *reinterpret_cast<float4*>(dst + A_CHUNK_BYTES) = make_float4(x0 - h.x, x1 - h.y, x2 - h.z, x3 - h.w);
+  }
+}
+
 // ---- shared-memory control block -------------------------------------------------------------------------------------
 struct Control {
   uint64_t full_x[NSTAGE];     // producers -> MMA   (count PROD_WARPS)
