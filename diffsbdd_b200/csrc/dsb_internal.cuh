@@ -237,6 +237,33 @@ __device__ __forceinline__ f32x2 silu2(f32x2 u) {
   return mul2(u, pk2(rcp_approx(a), rcp_approx(b)));
 }
 
+// SiLU of four values with TWO reciprocals instead of four: the 16-lane XU pipe (MUFU: 8 issue cycles per warp instruction
+// and sub-partition) is the busiest pipe of the edge kernels (2 SiLU per edge element = 4 MUFU), the FMA pipe is not.
+//   d_i = 1 + 2^{t_i},  r = 1 / (d_a d_b)  ->  1/d_a = r d_b,  1/d_b = r d_a          (elements 0,2 and 1,3 are paired)
+// The exponent argument is clamped to 64 (pre-activation >= -44.4, where SiLU(x) = x e^x is below 3e-18 in magnitude) so that
+// neither d nor, harmfully, the product can reach inf next to a finite partner (0 * inf); a product of exactly 2^128 gives
+// r = 0 and both results 0.  Relative error ~4e-7 (one rcp.approx and two roundings more than silu_f).
+__device__ __forceinline__ void silu4(f32x2& u01, f32x2& u23) {
+  const f32x2 c = pk2(-1.4426950408889634f, -1.4426950408889634f), one = pk2(1.0f, 1.0f);
+  float t0, t1, t2, t3;
+  upk2(mul2(u01, c), t0, t1); upk2(mul2(u23, c), t2, t3);
+  const f32x2 d01 = add2(pk2(ex2_approx(fminf(t0, 64.f)), ex2_approx(fminf(t1, 64.f))), one);
+  const f32x2 d23 = add2(pk2(ex2_approx(fminf(t2, 64.f)), ex2_approx(fminf(t3, 64.f))), one);
+  float p0, p1;
+  upk2(mul2(d01, d23), p0, p1);
+  const f32x2 r = pk2(rcp_approx(p0), rcp_approx(p1));
+  u01 = mul2(u01, mul2(r, d23));
+  u23 = mul2(u23, mul2(r, d01));
+}
+#ifndef DSB_SILU_PAIR
+#define DSB_SILU_PAIR 3          // bit 0: producers, bit 1: epilogues of the tensor-core edge kernels use silu4
+#endif
+template <bool PAIR>
+__device__ __forceinline__ void silu_pair(f32x2& u01, f32x2& u23) {
+  if constexpr (PAIR) silu4(u01, u23);
+  else { u01 = silu2(u01); u23 = silu2(u23); }
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

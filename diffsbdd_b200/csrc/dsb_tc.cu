@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
             a01 = add2(pk2(v[4 * q], v[4 * q + 1]), pk2(bb.x, bb.y));
             a23 = add2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(bb.z, bb.w));
           }
-          a01 = silu2(a01); a23 = silu2(a23);
+          silu_pair<(DSB_SILU_PAIR & 2) != 0>(a01, a23);
           upk2(a01, v[4 * q], v[4 * q + 1]); upk2(a23, v[4 * q + 2], v[4 * q + 3]);
           s01 = fma2(a01, pk2(ww.x, ww.y), s01); s23 = fma2(a23, pk2(ww.z, ww.w), s23);
         }
@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
                 const float4 t4 = *reinterpret_cast<const float4*>(tbm + pty[i] + hf * TKC);
                 u01 = add2(u01, pk2(t4.x, t4.y)); u23 = add2(u23, pk2(t4.z, t4.w));
               }
-              if (!(dbg & 128)) { u01 = silu2(u01); u23 = silu2(u23); }      // 128: instrumented builds only
+              if (!(dbg & 128)) silu_pair<(DSB_SILU_PAIR & 1) != 0>(u01, u23);      // 128: instrumented builds only
               store_pair<F16>(st + (F16 && (hf & 1) ? (so[i] ^ 64u) : so[i]), u01, u23);
             }
           }
