@@ -14,6 +14,8 @@
 //   warps 14-15 (edge kernels only) scalar warps: per-edge indices, distances and directions one tile ahead
 // Two shared-memory stages (96 KB each) and two 256-column TMEM accumulators: the epilogue of tile t overlaps the
 // main loop of tile t+1.
+#include <cstdlib>
+
 #include "dsb_tc.cuh"
 
 namespace dsb {
@@ -666,12 +668,39 @@ __device__ __forceinline__ void edge_scalars(const TcEdgeArgs& a, EdgeExtra<H>* 
 // are independent units that add into the same receiver sums: units, not edge tiles, are dealt round-robin to the CTAs (610 edge
 // tiles on 148 CTAs would leave 21 % of the machine idle in the last wave; 1220 units leave 9 %).  The j-th unit of a CTA uses
 // scalar set j % NSCAL and accumulator j & 1.
-template <bool COORD, bool F16, int H, bool TB>
+//
+// PAIR = true (3xFP16 only): the kernel runs as 74 CTA pairs (cluster of 2, tcgen05 cta_group::2).  A pair works on two edge
+// tiles at a time (M = 256: each CTA produces, and post-processes, its own 128 rows) and on ONE MLP for the whole launch, whose
+// second-layer weights stay in shared memory: each CTA holds the hi and lo images of its half of the H output columns (B is
+// split along N between the two CTAs: 128 KB per CTA at H = 256), loaded once before the first tile.  Against PAIR = false
+// this removes the per-tile weight stream (256 KB of bulk copies into shared memory per tile and SM) and a third of the tensor
+// core's operand reads (per MMA and CTA: A 4 KB + half of B 4 KB instead of 4 + 8) from the L1 data pipe, the busiest unit of
+// these kernels (profiles/r2b_edge_ncu.txt).  The leader CTA's MMA thread issues for both CTAs; the peer's producers and
+// epilogue warps arrive on the leader's full_x / epi_done barriers through the cluster address space, the commits are multicast.
+template <int H, bool PAIR>
+struct EdgeGeo {
+  static constexpr int STAGE_BYTES = PAIR ? 2 * A_CHUNK_BYTES : Geo<H>::STAGE_BYTES;      // PAIR: the ring holds A chunks only
+  static constexpr int HB = (H / 2) * 128;                                                // one k-chunk of this CTA's weight half (hi or lo)
+  static constexpr int W_BYTES = PAIR ? (H / TKC16) * 2 * HB : 0;                         // resident weight half: chunks x (hi | lo)
+  static constexpr uint32_t IDESC_F16_2CTA = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);   // D=F32, A=B=F16, N=H, M=256
+};
+template <int H, bool PAIR> constexpr size_t edge_smem_base() { return 1024 + (size_t)NSTAGE * EdgeGeo<H, PAIR>::STAGE_BYTES + EdgeGeo<H, PAIR>::W_BYTES + kControlBytes; }
+
+template <bool COORD, bool F16, int H, bool TB, bool PAIR>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) {
+  static_assert(!PAIR || F16, "the CTA-pair kernel keeps 3xFP16 weight halves resident; 3xTF32 images do not fit");
   using G = Geo<H>;
+  using EG = EdgeGeo<H, PAIR>;
   constexpr int TN = H;
   extern __shared__ uint8_t smem_raw[];
-  const Carve cv = carve_smem<H>(smem_raw);
+  Carve cv;
+  {
+    const uint32_t base = smem_u32(smem_raw);
+    cv.stages = reinterpret_cast<char*>(smem_raw) + ((1024u - (base & 1023u)) & 1023u);
+    cv.ctl = reinterpret_cast<Control*>(cv.stages + NSTAGE * EG::STAGE_BYTES + EG::W_BYTES);
+    cv.extra = reinterpret_cast<char*>(cv.ctl) + kControlBytes;
+  }
+  char* const wres = cv.stages + NSTAGE * EG::STAGE_BYTES;      // PAIR: resident weight half, [chunk][hi | lo][H/2 rows x 128 B]
   Control* ctl = cv.ctl;
   EdgeExtra<H>* ex = reinterpret_cast<EdgeExtra<H>*>(cv.extra);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -679,6 +708,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
   constexpr int halves = H / TKC;           // 32-k production steps per unit
   constexpr int HPC = F16 ? 2 : 1;             // production steps per pipeline chunk (stage)
   constexpr int chunks = halves / HPC;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;          // 0 = leader
+  // PAIR: pair p of npairs works on MLP p % nm for the whole launch (its weights stay resident) and on the tile pairs
+  // p / nm, p / nm + npairs / nm, ...; this CTA takes tile 2 * pair_unit + rank (a tile beyond the end is all padding)
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_pair = PAIR ? pair % nm : 0, pu0 = PAIR ? pair / nm : 0, pustride = PAIR ? npairs / nm : 1;
 
   pdl_trigger();
   for (int i = threadIdx.x; i < H; i += EDGE_THREADS) {
@@ -688,13 +722,63 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     }
     ex->wa[i] = a.wa ? a.wa[i] : 0.f;
   }
-  tc_begin(ctl, warp, SCAL_WARPS);        // contains the __syncthreads that publishes the vectors
+  if constexpr (PAIR) {
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < NSTAGE; ++s) { mbar_init(&ctl->full_x[s], 2 * PROD_WARPS); mbar_init(&ctl->full_w[s], 1); mbar_init(&ctl->empty[s], 1); }
+      for (int k = 0; k < 2; ++k) { mbar_init(&ctl->acc_full[k], 1); mbar_init(&ctl->epi_done[k], 2 * EPI_WARPS); }
+      for (int k = 0; k < 3; ++k) { mbar_init(&ctl->scal_full[k], SCAL_WARPS); mbar_init(&ctl->scal_empty[k], EPI_WARPS); }
+      mbar_init(&ctl->w_full, 1); mbar_init(&ctl->w_ready, 2);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_alloc2(&ctl->tmem_base, 512);
+    if (warp == TMA_WARP && lane == 0) {
+      // the resident weight half: constant data, requested before the dependency wait so it overlaps the predecessor's tail
+      mbar_arrive_expect_tx(&ctl->w_full, EG::W_BYTES);
+      const float* hi = a.W2hi[m_pair] + (size_t)rank * (EG::HB / 4);
+      const float* lo = a.W2lo[m_pair] + (size_t)rank * (EG::HB / 4);
+      for (int kc = 0; kc < chunks; ++kc) {
+        bulk_g2s(wres + (size_t)kc * 2 * EG::HB, hi + (size_t)kc * G::B_CHUNK_FLOATS, EG::HB, &ctl->w_full);
+        bulk_g2s(wres + (size_t)kc * 2 * EG::HB + EG::HB, lo + (size_t)kc * G::B_CHUNK_FLOATS, EG::HB, &ctl->w_full);
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();         // both CTAs' barriers are initialised before anyone arrives remotely; publishes the vectors
+    tc_fence_after();
+  } else {
+    tc_begin(ctl, warp, SCAL_WARPS);        // contains the __syncthreads that publishes the vectors
+  }
+  auto kernel_end = [&]() {
+    if constexpr (PAIR) {
+      tc_fence_before();
+      cluster_sync_all();       // the peer may still arrive on this CTA's barriers / the leader's MMAs read the peer's shared memory
+      if (warp == MMA_WARP) tmem_dealloc2(ctl->tmem_base, 512);
+    } else {
+      tc_end(ctl, warp);
+    }
+  };
   pdl_wait();                 // everything above touches only kernel arguments and constant weights
   const int E = a.vrow_ptr[a.n_rows];          // virtual rows: every receiver's edges start at a multiple of kRowChunk
-  const int n_units = ((E + TM - 1) / TM) * nm;
-  const int n_my = ((int)blockIdx.x < n_units) ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  if (n_my == 0) { tc_end(ctl, warp); return; }
-  auto unit_tile = [&](int j, int& m) { const int v = blockIdx.x + j * gridDim.x; const int t = v / nm; m = v - t * nm; return t; };
+  const int n_tiles_e = (E + TM - 1) / TM;
+  const int n_units = PAIR ? (n_tiles_e + 1) / 2 : n_tiles_e * nm;      // PAIR: tile pairs (of this pair's MLP)
+  const int u0 = PAIR ? pu0 : (int)blockIdx.x, ustride = PAIR ? pustride : (int)gridDim.x;
+  const int n_my = (u0 < n_units) ? (n_units - u0 + ustride - 1) / ustride : 0;
+  if (n_my == 0) {
+    if (PAIR && warp == TMA_WARP && lane == 0) mbar_wait(&ctl->w_full, 0);      // no shared memory may be freed under a bulk copy in flight
+    __syncwarp();
+    kernel_end();
+    return;
+  }
+  auto unit_tile = [&](int j, int& m) {
+    const int v = u0 + j * ustride;
+    if constexpr (PAIR) { m = m_pair; return 2 * v + rank; }
+    else { const int t = v / nm; m = v - t * nm; return t; }
+  };
+  // arrivals that the (leader's) MMA thread waits for
+  const uint32_t l_full_x = PAIR ? leader_addr(&ctl->full_x[0]) : 0u, l_epi_done = PAIR ? leader_addr(&ctl->epi_done[0]) : 0u;
+  auto arrive_full_x = [&](int s) { if constexpr (PAIR) mbar_arrive_cluster(l_full_x + 8u * (uint32_t)s); else mbar_arrive(&ctl->full_x[s]); };
+  auto arrive_epi_done = [&](int k) { if constexpr (PAIR) mbar_arrive_cluster(l_epi_done + 8u * (uint32_t)k); else mbar_arrive(&ctl->epi_done[k]); };
 
   if (warp < EPI_WARPS) {
     // ------------------------------------------------------------------------------------------ epilogue
@@ -720,7 +804,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       const int myrow = ex->row[par][warp * 32 + lane];
       if (tc_debug() & 4) {
         tc_fence_before(); __syncwarp();
-        if (lane == 0) { mbar_arrive(&ctl->epi_done[acc]); mbar_arrive(&ctl->scal_empty[par]); }
+        if (lane == 0) { arrive_epi_done(acc); mbar_arrive(&ctl->scal_empty[par]); }
         continue;
       }
       // pass 1: m = SiLU(acc + b2); s = wa . m   (GCL: attention logit; coord: phi, wa = w3)
@@ -833,7 +917,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&ctl->epi_done[acc]);
+        arrive_epi_done(acc);
         mbar_arrive(&ctl->scal_empty[par]);
       }
     }
@@ -908,7 +992,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
 #pragma unroll
       for (int kc = 0; kc < chunks; ++kc) {
         const int s = gc & 1;
-        char* st = cv.stages + (size_t)s * G::STAGE_BYTES;
+        char* st = cv.stages + (size_t)s * EG::STAGE_BYTES;
         if (pprof) t0 = tc_clock();
         mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);      // stage released by the MMAs that read it two chunks ago
         if (pprof) { t1 = tc_clock(); acc_wait += t1 - t0; }
@@ -940,7 +1024,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         if (pprof) { t2 = tc_clock(); acc_comp += t2 - t1; }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl->full_x[s]);
+        if (lane == 0) arrive_full_x(s);
         ++gc;
         if (pprof) acc_fence += tc_clock() - t2;
         if (kc + 1 < chunks) {
@@ -966,15 +1050,55 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       atomicAdd(&g_tc_prof[25], 1ull);
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) mma_role<F16, H>(ctl, cv.stages, n_my, chunks, COORD ? 2 : 1);
+    if constexpr (PAIR) {
+      if (lane == 0 && rank == 0) {
+        // the leader issues for the pair: per tile pair and chunk 4 k-steps x 3 split products, M = 256, operands at the same
+        // shared-memory offsets in both CTAs (A: ring stage; B: resident weight half, chunk kc)
+        const uint32_t tmem = ctl->tmem_base;
+        mbar_wait_cluster(&ctl->w_ready, 0);
+        uint32_t g = 0;
+        for (int j = 0; j < n_my; ++j) {
+          const int k = j & 1;
+          mbar_wait_cluster(&ctl->epi_done[k], ((j >> 1) & 1) ^ 1);      // accumulator drained by both CTAs' epilogues
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(k * ACC_STRIDE);
+#pragma unroll 1
+          for (int kc = 0; kc < chunks; ++kc, ++g) {
+            const int s = g & 1;
+            mbar_wait_cluster(&ctl->full_x[s], (g >> 1) & 1);            // both CTAs' producers filled stage s
+            tc_fence_after();
+            const uint32_t xhi = smem_u32(cv.stages + (size_t)s * EG::STAGE_BYTES), xlo = xhi + A_CHUNK_BYTES;
+            const uint32_t whi = smem_u32(wres + (size_t)kc * 2 * EG::HB), wlo = whi + EG::HB;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ko = ks * 32;
+              umma_f16_2cta(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), EG::IDESC_F16_2CTA, (kc == 0 && ks == 0) ? 0u : 1u);
+              umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), EG::IDESC_F16_2CTA, 1u);
+              umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), EG::IDESC_F16_2CTA, 1u);
+            }
+            umma_commit_2cta(&ctl->empty[s]);         // stage reusable in both CTAs once these MMAs have read it
+          }
+          umma_commit_2cta(&ctl->acc_full[k]);        // both CTAs' accumulators complete
+        }
+      }
+    } else {
+      if (lane == 0) mma_role<F16, H>(ctl, cv.stages, n_my, chunks, COORD ? 2 : 1);
+    }
     __syncwarp();
   } else if (warp == TMA_WARP) {
-    if (lane == 0) {
-      uint32_t gc = 0;
-      for (int j = 0; j < n_my; ++j) {
-        int m;
-        unit_tile(j, m);
-        tma_role<H>(ctl, cv.stages, a.W2hi[m], a.W2lo[m], gc, chunks);
+    if constexpr (PAIR) {
+      if (lane == 0) {
+        mbar_wait(&ctl->w_full, 0);                   // this CTA's weight half has landed
+        mbar_arrive_cluster(leader_addr(&ctl->w_ready));
+      }
+    } else {
+      if (lane == 0) {
+        uint32_t gc = 0;
+        for (int j = 0; j < n_my; ++j) {
+          int m;
+          unit_tile(j, m);
+          tma_role<H>(ctl, cv.stages, a.W2hi[m], a.W2lo[m], gc, chunks);
+        }
       }
     }
     __syncwarp();
@@ -994,14 +1118,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       if (lane == 0) mbar_arrive(&ctl->scal_full[par]);
     }
   }
-  tc_end(ctl, warp);
+  kernel_end();
 }
 
 // =====================================================================================================
 // launchers
 // =====================================================================================================
 template <int H> static size_t gemm_smem_bytes() { return tc_smem_base<H>() + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE; }
-template <int H> static size_t edge_smem_bytes() { return tc_smem_base<H>() + sizeof(EdgeExtra<H>); }
+template <int H, bool PAIR> static size_t edge_smem_bytes() {
+  static_assert(edge_smem_base<H, PAIR>() + sizeof(EdgeExtra<H>) <= 232448, "edge kernel exceeds the 227 KB of shared memory per CTA");
+  return edge_smem_base<H, PAIR>() + sizeof(EdgeExtra<H>);
+}
+// The CTA-pair (weight-stationary) form of the 3xFP16 edge kernels is the default; DSB_EDGE_PAIR=0 in the environment selects the
+// single-CTA kernels that stream the weight images (A/B measurements; 3xTF32 always uses them).
+static bool edge_pair_enabled() {
+  static const int v = [] { const char* e = getenv("DSB_EDGE_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v != 0;
+}
 
 bool tc_width_supported(int H) { return H == 128 || H == 192 || H == 256; }
 
@@ -1018,19 +1151,23 @@ static int dispatch_width(int H, Fn&& fn) {
 
 int configure_tc_kernels(int H) {
   return dispatch_width(H, [&]<int W>() -> int {
-    const int gs = (int)gemm_smem_bytes<W>(), es = (int)edge_smem_bytes<W>();
+    const int gs = (int)gemm_smem_bytes<W>(), es = (int)edge_smem_bytes<W, false>(), ep = (int)edge_smem_bytes<W, true>();
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
-    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, false, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ep));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ep));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ep));
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<true, true, W, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ep));
     return 0;
   });
 }
@@ -1089,9 +1226,14 @@ int launch_tc_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   a.wr[0] = w.wr; a.wr0[0] = w.wr0; a.tb[0] = w.tb; a.b2[0] = w.b2;
   a.wa = w.wa; a.ba = w.ba; a.agg = ws.agg; a.status = status;
   return dispatch_width(d->cfg.hidden_nf, [&]<int W>() -> int {
-    auto kern = w.tb ? (f16 ? tc_edge_kernel<false, true, W, true> : tc_edge_kernel<false, false, W, true>)
-                     : (f16 ? tc_edge_kernel<false, true, W, false> : tc_edge_kernel<false, false, W, false>);
-    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W>(), s, a));
+    if (f16 && edge_pair_enabled() && d->num_sms >= 2) {
+      DSB_CUDA_OK(launch_k_pair(w.tb ? tc_edge_kernel<false, true, W, true, true> : tc_edge_kernel<false, true, W, false, true>,
+                                d->num_sms & ~1, EDGE_THREADS, edge_smem_bytes<W, true>(), s, a));
+      return 0;
+    }
+    auto kern = w.tb ? (f16 ? tc_edge_kernel<false, true, W, true, false> : tc_edge_kernel<false, false, W, true, false>)
+                     : (f16 ? tc_edge_kernel<false, true, W, false, false> : tc_edge_kernel<false, false, W, false, false>);
+    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W, false>(), s, a));
     return 0;
   });
 }
@@ -1112,9 +1254,15 @@ int launch_tc_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace&
   a.wa = w.w3; a.ba = nullptr;
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh; a.xagg = ws.xagg; a.status = status;
   return dispatch_width(c.hidden_nf, [&]<int W>() -> int {
-    auto kern = w.tb[0] ? (f16 ? tc_edge_kernel<true, true, W, true> : tc_edge_kernel<true, false, W, true>)
-                        : (f16 ? tc_edge_kernel<true, true, W, false> : tc_edge_kernel<true, false, W, false>);
-    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W>(), s, a));
+    const int npairs = d->num_sms / 2;
+    if (f16 && edge_pair_enabled() && npairs >= a.nm && npairs % a.nm == 0) {       // every pair keeps ONE MLP's weights resident
+      DSB_CUDA_OK(launch_k_pair(w.tb[0] ? tc_edge_kernel<true, true, W, true, true> : tc_edge_kernel<true, true, W, false, true>,
+                                2 * npairs, EDGE_THREADS, edge_smem_bytes<W, true>(), s, a));
+      return 0;
+    }
+    auto kern = w.tb[0] ? (f16 ? tc_edge_kernel<true, true, W, true, false> : tc_edge_kernel<true, false, W, true, false>)
+                        : (f16 ? tc_edge_kernel<true, true, W, false, false> : tc_edge_kernel<true, false, W, false, false>);
+    DSB_CUDA_OK(launch_k(kern, d->num_sms, EDGE_THREADS, edge_smem_bytes<W, false>(), s, a));
     return 0;
   });
 }

@@ -189,6 +189,65 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- CTA pair (cluster of 2, tcgen05 cta_group::2) ----------------------------------------------------------------------
+// The leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 for both: M = 256 = the two CTAs' 128 operand rows each (A
+// descriptor: the same shared-memory offset in both CTAs), B = N/2 rows per CTA at one offset, accumulators in each CTA's own
+// TMEM.  Hand-offs that involve the other CTA are mbarrier arrives on the leader's barriers through the cluster address space
+// (release / acquire at cluster scope) and multicast commits.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the leader CTA's copy of a shared-memory object
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+// Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive: what is handed over lives in the arriving
+// CTA's own shared memory / TMEM (made visible to the async proxy by fence.proxy.async resp. ordered by tcgen05.fence before
+// the arrive) and is consumed by tensor-core hardware, not by another SM's loads.  The .release.cluster form compiles to
+// MEMBAR.ALL.GPU, which would stall every hand-off on the thread's prefetched gathers.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 17)) { printf("dsb tc: cluster mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {   // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued MMAs of this thread arrive on the barrier at this shared-memory offset in BOTH CTAs when they complete
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // round-to-nearest (ties away) to the 19-bit TF32 container with two integer-pipe instructions (cvt.rna.tf32.f32
 // would occupy the 16-lane XU pipe that the SiLU exponentials already saturate)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
@@ -281,6 +340,8 @@ struct Control {
   uint64_t epi_done[2];        // epilogue -> MMA, producers (count EPI_WARPS)
   uint64_t scal_full[3];       // scalar warps -> producers, epilogue (count SCAL_WARPS): per-edge scalars of the tile are in shared memory
   uint64_t scal_empty[3];      // epilogue -> scalar warps (count EPI_WARPS): scalar buffers of the tile may be overwritten
+  uint64_t w_full;             // CTA-pair edge kernels: bulk copies of this CTA's resident weight half (count 1 + tx bytes)
+  uint64_t w_ready;            // ... leader only: both CTAs' weight halves are in shared memory (count 2)
   uint32_t tmem_base;
   uint32_t pad;
 };
