@@ -811,6 +811,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
   const bool conditional = dm.n_coord_rows < dm.N;
   static const bool no_fused_mlp = getenv("DSB_NO_FUSED_MLP") != nullptr;      // A/B timing switch (two node GEMMs instead)
   for (int l = 0; l < c.n_layers; ++l) {
+    bool fused_block = false;
     for (int sub = 0; sub < c.inv_sublayers; ++sub) {
       const GclW& G = dyn->w.gcl[l][sub];
       if (!(sub == 0 && l > 0)) {      // otherwise produced by the previous block's merged GEMM
@@ -823,7 +824,13 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       DSB_TRY((mm & 2) ? launch_tc_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, f16, status, s) : launch_edge_gcl(dyn, dm, ws, G, xcur, pv_gcl, s));
       // node_model: h + W4 SiLU(W3 [h | agg/norm] + b3) + b4   (egnn_new.py:48-58)
       mark(KC_NODE_GEMM);
-      if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !no_fused_mlp) {
+      const EquivW& Qb = dyn->w.eq[l];
+      if ((mm & 1) && sub == c.inv_sublayers - 1 && G.iW3.h_hi && G.iW4.h_hi && Qb.iW1.h_hi && !no_fused_mlp && tc_node_block_available(H, f16)) {
+        // node_model and the merged first-layer GEMM of this block in one CTA-pair kernel (h converted to operand format once)
+        DSB_TRY(launch_tc_node_block(dyn, dm, ws, G, Qb, ws.P, ldP, conditional ? dm.n_coord_rows : 0, conditional ? nrecv : 0, s));
+        launches += 3;
+        fused_block = true;
+      } else if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !no_fused_mlp) {
         DSB_TRY(launch_tc_node_mlp(dyn, dm, ws, G, f16, status, s));        // both layers in one kernel, hidden stays on chip
         launches += 2;
       } else {
@@ -838,9 +845,11 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     // edge first layer.  In conditional mode the receiver-side coord columns are needed for ligand rows only.
     const EquivW& Q = dyn->w.eq[l];
     mark(KC_NODE_GEMM);
+    if (!fused_block) {
     GemmArgs g4 = {ws.h, H, H, nullptr, 0, 0, 1.f, Q.W1, Q.nq + Q.np, Q.b1, nullptr, 0, ws.P, ldP, dm.N, Q.nq + Q.np, 0, nullptr, 0,
                    conditional ? dm.n_coord_rows : 0, conditional ? nrecv : 0};
     DSB_TRY(gemm(g4, Q.iW1));
+    }
     mark(KC_EDGE_COORD);
     DSB_TRY((mm & 4) ? launch_tc_edge_coord(dyn, dm, ws, Q, xcur, pv_coord, f16, status, s) : launch_edge_coord(dyn, dm, ws, Q, xcur, pv_coord, s));
     float4* xnext = ws.xbuf[1 + (l & 1)];

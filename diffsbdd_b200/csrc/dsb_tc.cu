@@ -585,6 +585,415 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
 }
 
 // =====================================================================================================
+// fused node block (CTA pairs, 3xFP16): everything between the two edge kernels of an equivariant block in one launch.
+//   phase 1   hid = SiLU(W3 [h | agg/norm] + b3)            (egnn_new.py:48-58, K = 2H)   -> accumulator 0
+//   phase 2   h  <- h + W4 hid + b4, agg re-armed                                          -> accumulator 1
+//   phase 3   P   = Wq h + bq for every live H-wide column tile of the merged first layers (this block's coordinate MLPs |
+//             the next block's edge MLP)                                      -> accumulators alternate
+// A CTA pair owns 2 x 128 node rows (tcgen05 cta_group::2, M = 256; each CTA keeps its own rows).  The A operand of phases 2
+// and 3 never leaves the SM: the epilogue warps write SiLU(hid) resp. the new h, already split and swizzled, into the
+// resident A slots (K = H = 4 chunks of 32 KB), so h is converted to the 3xFP16 operand format ONCE per block instead of once
+// per column tile (the separate merged GEMM rebuilt its A operand for each of its 4-6 column tiles, and its producers, not the
+// tensor pipe, bounded it).  Phase 1 streams its 8 A chunks through the same slots.  Each CTA streams only its half of the
+// weight columns (B split along N): 32 KB per k-chunk and CTA.
+// Barriers: full_a / epi_done / w_peer live in the leader (cluster rank 0), whose MMA thread issues for both CTAs; the peer's
+// warps arrive through the cluster address space; e0 / e3 / empty_w / acc_full are multicast commits.  A slot is written four
+// times per item (phase-1 chunks 0..3, chunks 4..7, hid, new h): full_a completes four times per item (parity = write & 1).
+// A parity wait can only tell "the phase I expect" from "the next one", so every waiter follows its barrier phase by phase:
+// the producers' second write waits for e0 (phase-1 chunk 0..3 read), their first write of the NEXT item for e3 (last
+// phase-3 read), one completion per item each; the epilogue's writes are ordered by acc_full (all MMAs of the phase done).
+// =====================================================================================================
+// x / d from the reciprocal and one residual correction: q = x r; q += (x - q d) r.  Correctly rounded except for results within
+// ~2^-46 relative of a rounding boundary (the IEEE division it replaces was 20 % of the producers' instructions); finite inputs only.
+__device__ __forceinline__ float div_by(float x, float d, float r) { const float q = x * r; return fmaf(fmaf(-q, d, x), r, q); }
+
+struct TcBlockArgs {
+  float* h; int ldh;                          // [M][H], updated in place
+  float* agg; int ldagg; float div;           // raw receiver sums: A2 of phase 1 (exact division), zeroed by phase 2
+  const float *W3hi, *W3lo, *W4hi, *W4lo;     // node_mlp images
+  const float *Wqhi, *Wqlo;                   // merged first-layer images, [Nn/H][H/64][H x 128 B]
+  const float *b3, *b4, *bq;
+  float inv3, inv4, invq, s4;                 // 1 / weight scale per image (powers of two); s4 = 1 / inv4
+  float* P; int ldp; int Nn;
+  int M; int dead_mt; int dead_nt;            // column tiles < dead_nt are not needed for row tiles >= dead_mt
+};
+struct BlockControl {
+  uint64_t full_a[4], e0[4], e3[4];
+  uint64_t pre_done;                          // leader: the phase-2 accumulator holds (h + b4) * s4 in both CTAs (count 2 * EPI_WARPS)
+  uint64_t full_w[2], w_peer[2], empty_w[2];
+  uint64_t acc_full[2], epi_done[2];
+  uint32_t tmem_base, pad;
+};
+static_assert(sizeof(BlockControl) <= kControlBytes, "BlockControl grew");
+template <int H> constexpr size_t block_smem_bytes() {
+  return 1024 + (size_t)(H / TKC16) * 2 * A_CHUNK_BYTES + 2 * (size_t)(H * 128) + kControlBytes + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE;
+}
+
+template <int H>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArgs g) {
+  using G = Geo<H>;
+  constexpr int C1 = 2 * H / TKC16, C2 = H / TKC16;      // k-chunks of phase 1; of phase 2 and of one column tile of phase 3
+  constexpr int NSLOT = C2;                                 // resident A slots (K = H)
+  constexpr int SLOT_BYTES = 2 * A_CHUNK_BYTES;             // hi | lo
+  constexpr int HB = (H / 2) * 128;                         // one k-chunk of this CTA's weight-column half (hi or lo)
+  constexpr int WST_BYTES = 2 * HB;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);   // F16 x F16 -> F32, N = H, M = 256
+  static_assert(C1 == 2 * NSLOT && NSLOT <= 4, "slot ring");
+  extern __shared__ uint8_t smem_raw[];
+  char* const slots = reinterpret_cast<char*>(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  char* const wst = slots + NSLOT * SLOT_BYTES;
+  BlockControl* ctl = reinterpret_cast<BlockControl*>(wst + 2 * WST_BYTES);
+  float* const Tall = reinterpret_cast<float*>(reinterpret_cast<char*>(ctl) + kControlBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank(), pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int ntm = (g.M + TM - 1) / TM, nmp = (ntm + 1) / 2, ntn = g.Nn / H;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) { mbar_init(&ctl->full_a[k], 2 * PROD_WARPS); mbar_init(&ctl->e0[k], 1); mbar_init(&ctl->e3[k], 1); }
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&ctl->full_w[k], 1); mbar_init(&ctl->w_peer[k], 1); mbar_init(&ctl->empty_w[k], 1);
+      mbar_init(&ctl->acc_full[k], 1); mbar_init(&ctl->epi_done[k], 2 * EPI_WARPS);
+    }
+    mbar_init(&ctl->pre_done, 2 * EPI_WARPS);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_alloc2(&ctl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  auto kernel_end = [&]() {
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == MMA_WARP) tmem_dealloc2(ctl->tmem_base, 512);
+  };
+  pdl_wait();
+  const int n_items = pair < nmp ? (nmp - pair + npairs - 1) / npairs : 0;
+  if (n_items == 0) { kernel_end(); return; }
+  auto item_mp = [&](int it) { return pair + it * npairs; };
+  // first live column tile of an item: both row tiles of the pair must lie in the dead region for a column tile to be skipped
+  auto item_nt0 = [&](int it) { return (g.dead_nt > 0 && 2 * item_mp(it) >= g.dead_mt) ? g.dead_nt : 0; };
+  const uint32_t l_full_a = leader_addr(&ctl->full_a[0]), l_epi_done = leader_addr(&ctl->epi_done[0]), l_w_peer = leader_addr(&ctl->w_peer[0]);
+  const uint32_t l_pre_done = leader_addr(&ctl->pre_done);
+  auto arrive_n = [&](uint32_t addr, uint32_t n) { asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;" ::"r"(addr), "r"(n) : "memory"); };
+
+  if (warp < EPI_WARPS) {
+    // ---------------------------------------------------------------------------------------------- epilogue warps
+    float* T = Tall + warp * (32 * GEMM_T_STRIDE);
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;
+    const uint32_t tbase = ctl->tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int myrow = warp * 32 + lane;
+    uint32_t u = 0;                              // accumulator uses so far (use u: accumulator u & 1, phase (u >> 1) & 1)
+    for (int it = 0; it < n_items; ++it) {
+      const int m0 = (2 * item_mp(it) + rank) * TM;
+      // ---- while phase 1 runs: the residual goes INTO the phase-2 accumulator, (h + b4) * s4 (s4 a power of two: exact), and
+      // the phase-2 MMAs accumulate on top of it.  The phase-2 epilogue then needs no global load before it can hand the new h
+      // to phase 3 (it used to wait an L2 round trip per 32 columns, 20 k cycles per item on the MMA thread's critical path).
+      // Row-per-thread loads: 32 rows x 16 bytes per instruction, each row's 128-byte line reused by the next 7 loads.
+      {
+        const uint32_t taddr = tbase + (uint32_t)(((u + 1) & 1) * ACC_STRIDE);      // free: this warp drained its previous use
+        const int row = m0 + myrow;
+        const float* hr = g.h + (size_t)row * g.ldh;
+        const f32x2 sp = pk2(g.s4, g.s4);
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          float v[32];
+#pragma unroll
+          for (int p8 = 0; p8 < 8; ++p8) {
+            const float4 x = row < g.M ? *reinterpret_cast<const float4*>(hr + cb * 32 + 4 * p8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b4 + cb * 32 + 4 * p8));
+            upk2(mul2(add2(pk2(x.x, x.y), pk2(bb.x, bb.y)), sp), v[4 * p8], v[4 * p8 + 1]);
+            upk2(mul2(add2(pk2(x.z, x.w), pk2(bb.z, bb.w)), sp), v[4 * p8 + 2], v[4 * p8 + 3]);
+          }
+          tmem_st32(taddr + cb * 32, v);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_pre_done);
+      }
+      // ---- phase-1 epilogue = producer of the phase-2 A operand: SiLU(acc * inv3 + b3) -> slots (third write of a slot)
+      {
+        mbar_wait(&ctl->acc_full[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tbase + (uint32_t)((u & 1) * ACC_STRIDE);
+        const f32x2 ip = pk2(g.inv3, g.inv3);
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int kc = cb >> 1;
+          char* st = slots + (size_t)kc * SLOT_BYTES;
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int p8 = 0; p8 < 8; ++p8) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b3 + cb * 32 + 4 * p8));
+            f32x2 x01 = fma2(pk2(v[4 * p8], v[4 * p8 + 1]), ip, pk2(bb.x, bb.y));
+            f32x2 x23 = fma2(pk2(v[4 * p8 + 2], v[4 * p8 + 3]), ip, pk2(bb.z, bb.w));
+            silu_pair<true>(x01, x23);
+            float4 x;
+            upk2(x01, x.x, x.y); upk2(x23, x.z, x.w);
+            store_piece<true>(st, myrow, cb & 1, p8, x);
+          }
+          if (cb & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) arrive_n(l_full_a + 8u * (uint32_t)kc, PROD_WARPS / EPI_WARPS);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (u & 1));
+        ++u;
+      }
+      // ---- phase-2 epilogue: new h = acc * inv4 (the accumulator started from (h + b4) * s4).  First the phase-3 A operand
+      // (fourth write of a slot; phase 3 starts as soon as all four slots are handed over), then the global side: h in place,
+      // aggregate re-armed, each 32x32 block through the per-warp buffer so that 8 lanes cover 128 contiguous bytes of a row.
+      {
+        mbar_wait(&ctl->acc_full[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tbase + (uint32_t)((u & 1) * ACC_STRIDE);
+        const f32x2 ip = pk2(g.inv4, g.inv4);
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int kc = cb >> 1;
+          char* st = slots + (size_t)kc * SLOT_BYTES;
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int p8 = 0; p8 < 8; ++p8) {
+            float4 x;
+            upk2(mul2(pk2(v[4 * p8], v[4 * p8 + 1]), ip), x.x, x.y); upk2(mul2(pk2(v[4 * p8 + 2], v[4 * p8 + 3]), ip), x.z, x.w);
+            store_piece<true>(st, myrow, cb & 1, p8, x);
+          }
+          if (cb & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) arrive_n(l_full_a + 8u * (uint32_t)kc, PROD_WARPS / EPI_WARPS);
+          }
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int n = cb * 32 + tc4;
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + tr;
+            const int row = m0 + warp * 32 + rl;
+            const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+            float4 o;
+            upk2(mul2(pk2(x.x, x.y), ip), o.x, o.y); upk2(mul2(pk2(x.z, x.w), ip), o.z, o.w);
+            if (row < g.M) {
+              *reinterpret_cast<float4*>(g.h + (size_t)row * g.ldh + n) = o;
+              *reinterpret_cast<float4*>(g.agg + (size_t)row * g.ldagg + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (u & 1));
+        ++u;
+      }
+      // ---- phase-3 epilogues: P[:, column tile] = acc * invq + bq
+      for (int nt = item_nt0(it); nt < ntn; ++nt) {
+        mbar_wait(&ctl->acc_full[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tbase + (uint32_t)((u & 1) * ACC_STRIDE);
+        const f32x2 ip = pk2(g.invq, g.invq);
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int n = nt * H + cb * 32 + tc4;
+          const float4 bias = __ldg(reinterpret_cast<const float4*>(g.bq + n));
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const f32x2 b01 = pk2(bias.x, bias.y), b23 = pk2(bias.z, bias.w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + tr;
+            const int row = m0 + warp * 32 + rl;
+            const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+            float4 o;
+            upk2(fma2(pk2(x.x, x.y), ip, b01), o.x, o.y); upk2(fma2(pk2(x.z, x.w), ip, b23), o.z, o.w);
+            if (row < g.M) *reinterpret_cast<float4*>(g.P + (size_t)row * g.ldp + n) = o;
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (u & 1));
+        ++u;
+      }
+    }
+  } else if (warp < MMA_WARP) {
+    // ---------------------------------------------------------------------------------------------- producers: phase-1 A chunks
+    // [h | agg / norm] rows of this CTA's tile, 64 k per chunk, two register sets (loads two chunks ahead, issued after the
+    // proxy fence: see tc_node_gemm_kernel)
+    const int ptid = threadIdx.x - EPI_WARPS * 32;
+    const int pw = ptid >> 5, sr = lane >> 3, pc = lane & 7;
+    const int total = n_items * C1;
+    const float rdiv = __frcp_rn(g.div);
+    auto load_chunk = [&](int j, float4 (&buf)[2][4]) {
+      const int it = j / C1, kc = j - it * C1;
+      const int m0 = (2 * item_mp(it) + rank) * TM;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = (kc * 2 + hh) * TKC + 4 * pc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + 16 * pw + 4 * sr + i;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < g.M) x = k < H ? *reinterpret_cast<const float4*>(g.h + (size_t)m * g.ldh + k)
+                                    : *reinterpret_cast<const float4*>(g.agg + (size_t)m * g.ldagg + (k - H));
+          buf[hh][i] = x;
+        }
+      }
+    };
+    auto stage_chunk = [&](int j, float4 (&buf)[2][4]) {
+      const int it = j / C1, kc = j - it * C1;
+      const int slot = kc % NSLOT;
+      if (kc >= NSLOT) mbar_wait(&ctl->e0[slot], (uint32_t)it & 1u);            // second write of the slot: phase-1 chunk kc - NSLOT was read
+      else if (it > 0) mbar_wait(&ctl->e3[slot], (uint32_t)(it - 1) & 1u);     // first write: the previous item's phase 3 is done with it
+      char* st = slots + (size_t)slot * SLOT_BYTES;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const bool second = (kc * 2 + hh) * TKC + 4 * pc >= H;          // aggregate columns: exact division by the normalisation
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 x = buf[hh][i];
+          if (second) { x.x = div_by(x.x, g.div, rdiv); x.y = div_by(x.y, g.div, rdiv); x.z = div_by(x.z, g.div, rdiv); x.w = div_by(x.w, g.div, rdiv); }
+          store_piece<true>(st, 16 * pw + 4 * sr + i, hh, pc, x);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_full_a + 8u * (uint32_t)slot);
+      if (j + 2 < total) load_chunk(j + 2, buf);
+    };
+    float4 bufA[2][4], bufB[2][4];
+    load_chunk(0, bufA);
+    if (total > 1) load_chunk(1, bufB);
+    for (int j = 0; j < total; j += 2) {
+      stage_chunk(j, bufA);
+      if (j + 1 < total) stage_chunk(j + 1, bufB);
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0 && rank == 0) {
+      // -------------------------------------------------------------------------------------------- MMA issuer (leader)
+      const uint32_t tmem = ctl->tmem_base;
+      uint32_t gw = 0, u = 0;
+      // cycle accounting (instrumented library, flag 512): g_tc_prof[48 + 4 * phase + {0: wait A, 1: wait W, 2: wait peer's W, 3: issue}],
+      // [60] accumulator waits, [61] items, [62] whole loop
+      const bool bprof = (tc_debug() & 512) != 0;
+      long long w_a[3] = {0, 0, 0}, w_w[3] = {0, 0, 0}, w_p[3] = {0, 0, 0}, w_i[3] = {0, 0, 0}, w_acc = 0;
+      int ph = 0;
+      const long long b0 = bprof ? tc_clock() : 0;
+      auto chunk = [&](uint32_t d, int slot, uint32_t a_parity, bool wait_a, bool first, uint64_t* release_a) {
+        const int s = gw & 1;
+        const uint32_t par = (gw >> 1) & 1;
+        long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (bprof) q0 = tc_clock();
+        if (wait_a) mbar_wait_cluster(&ctl->full_a[slot], a_parity);
+        if (bprof) q1 = tc_clock();
+        mbar_wait(&ctl->full_w[s], par);
+        if (bprof) q2 = tc_clock();
+        mbar_wait_cluster(&ctl->w_peer[s], par);
+        if (bprof) { q3 = tc_clock(); w_a[ph] += q1 - q0; w_w[ph] += q2 - q1; w_p[ph] += q3 - q2; }
+        tc_fence_after();
+        const uint32_t xhi = smem_u32(slots + (size_t)slot * SLOT_BYTES), xlo = xhi + A_CHUNK_BYTES;
+        const uint32_t whi = smem_u32(wst + (size_t)s * WST_BYTES), wlo = whi + HB;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ko = ks * 32;
+          umma_f16_2cta(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC, (first && ks == 0) ? 0u : 1u);
+          umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC, 1u);
+          umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC, 1u);
+        }
+        umma_commit_2cta(&ctl->empty_w[s]);
+        if (release_a) umma_commit_2cta(release_a);
+        if (bprof) w_i[ph] += tc_clock() - q3;
+        ++gw;
+      };
+      auto begin_use = [&]() {
+        const long long q0 = bprof ? tc_clock() : 0;
+        mbar_wait_cluster(&ctl->epi_done[u & 1], ((u >> 1) & 1) ^ 1);     // accumulator drained by both CTAs' epilogue warps
+        if (bprof) w_acc += tc_clock() - q0;
+        tc_fence_after();
+        return tmem + (uint32_t)((u & 1) * ACC_STRIDE);
+      };
+      auto end_use = [&]() { umma_commit_2cta(&ctl->acc_full[u & 1]); ++u; };
+      for (int it = 0; it < n_items; ++it) {
+        ph = 0;
+        uint32_t d = begin_use();
+        for (int kc = 0; kc < C1; ++kc) chunk(d, kc % NSLOT, kc < NSLOT ? 0u : 1u, true, kc == 0, kc < NSLOT ? &ctl->e0[kc] : nullptr);     // slot writes 1, 2
+        end_use();
+        ph = 1;
+        d = begin_use();
+        mbar_wait_cluster(&ctl->pre_done, (uint32_t)it & 1u);          // the accumulator holds the residual in both CTAs
+        tc_fence_after();
+        for (int kc = 0; kc < C2; ++kc) chunk(d, kc, 0u, true, false, nullptr);                                // slot write 3 (hid); accumulates onto the residual
+        end_use();
+        const int nt0 = item_nt0(it);
+        ph = 2;
+        for (int nt = nt0; nt < ntn; ++nt) {
+          d = begin_use();
+          for (int kc = 0; kc < C2; ++kc) chunk(d, kc, 1u, nt == nt0, kc == 0, nt == ntn - 1 ? &ctl->e3[kc] : nullptr);   // slot write 4 (new h)
+          end_use();
+        }
+      }
+      if (bprof) {
+        for (int k = 0; k < 3; ++k) {
+          atomicAdd(&g_tc_prof[48 + 4 * k + 0], (unsigned long long)w_a[k]); atomicAdd(&g_tc_prof[48 + 4 * k + 1], (unsigned long long)w_w[k]);
+          atomicAdd(&g_tc_prof[48 + 4 * k + 2], (unsigned long long)w_p[k]); atomicAdd(&g_tc_prof[48 + 4 * k + 3], (unsigned long long)w_i[k]);
+        }
+        atomicAdd(&g_tc_prof[60], (unsigned long long)w_acc); atomicAdd(&g_tc_prof[61], (unsigned long long)n_items);
+        atomicAdd(&g_tc_prof[62], (unsigned long long)(tc_clock() - b0));
+      }
+    } else if (lane == 0) {
+      // peer CTA: forward "my weight half of chunk gw has landed" to the leader
+      uint32_t total = 0;
+      for (int it = 0; it < n_items; ++it) total += C1 + C2 + (uint32_t)(ntn - item_nt0(it)) * C2;
+      for (uint32_t gw = 0; gw < total; ++gw) {
+        mbar_wait(&ctl->full_w[gw & 1], (gw >> 1) & 1);
+        mbar_arrive_cluster(l_w_peer + 8u * (gw & 1));
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      // -------------------------------------------------------------------------------------------- weight stream (both CTAs)
+      uint32_t gw = 0;
+      auto load = [&](const float* hi, const float* lo, int kc) {
+        const int s = gw & 1;
+        mbar_wait(&ctl->empty_w[s], ((gw >> 1) & 1) ^ 1);
+        char* dst = wst + (size_t)s * WST_BYTES;
+        mbar_arrive_expect_tx(&ctl->full_w[s], WST_BYTES);
+        bulk_g2s(dst, hi + (size_t)kc * G::B_CHUNK_FLOATS + (size_t)rank * (HB / 4), HB, &ctl->full_w[s]);
+        bulk_g2s(dst + HB, lo + (size_t)kc * G::B_CHUNK_FLOATS + (size_t)rank * (HB / 4), HB, &ctl->full_w[s]);
+        ++gw;
+      };
+      for (int it = 0; it < n_items; ++it) {
+        for (int kc = 0; kc < C1; ++kc) load(g.W3hi, g.W3lo, kc);
+        for (int kc = 0; kc < C2; ++kc) load(g.W4hi, g.W4lo, kc);
+        for (int nt = item_nt0(it); nt < ntn; ++nt)
+          for (int kc = 0; kc < C2; ++kc) load(g.Wqhi + (size_t)nt * C2 * G::B_CHUNK_FLOATS, g.Wqlo + (size_t)nt * C2 * G::B_CHUNK_FLOATS, kc);
+      }
+    }
+    __syncwarp();
+  }
+  kernel_end();
+}
+
+// =====================================================================================================
 // edge kernels
 // =====================================================================================================
 // unroll factors of the epilogue loops (overridable for tuning builds: -DDSB_E1_UNROLL=... etc.)
@@ -1156,6 +1565,8 @@ int configure_tc_kernels(int H) {
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_mlp_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
+    static_assert(block_smem_bytes<W>() <= 232448, "node block kernel exceeds shared memory");
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_block_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes<W>()));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
@@ -1212,6 +1623,32 @@ int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   const int grid = ntm < d->num_sms ? ntm : d->num_sms;
   return dispatch_width(H, [&]<int W>() -> int {
     DSB_CUDA_OK(launch_k(f16 ? tc_node_mlp_kernel<true, W> : tc_node_mlp_kernel<false, W>, grid, TC_THREADS, gemm_smem_bytes<W>(), s, a));
+    return 0;
+  });
+}
+
+// node_model of GCL `w` followed by the merged first-layer GEMM `q` of the same block (nullptr: none), one launch
+bool tc_node_block_available(int H, bool f16) {
+  static const int on = [] { const char* e = getenv("DSB_NODE_BLOCK"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on && f16 && tc_width_supported(H);
+}
+int launch_tc_node_block(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const EquivW& q, float* P, int ldp,
+                         int dead_rows_from, int dead_cols, cudaStream_t s) {
+  if (dm.N == 0) return 0;
+  const int H = d->cfg.hidden_nf;
+  TcBlockArgs a = {};
+  a.h = ws.h; a.ldh = H; a.agg = ws.agg; a.ldagg = H; a.div = d->cfg.normalization_factor;
+  a.W3hi = w.iW3.h_hi; a.W3lo = w.iW3.h_lo; a.W4hi = w.iW4.h_hi; a.W4lo = w.iW4.h_lo;
+  a.Wqhi = q.iW1.h_hi; a.Wqlo = q.iW1.h_lo;
+  a.b3 = w.b3; a.b4 = w.b4; a.bq = q.b1;
+  a.inv3 = w.iW3.h_inv; a.inv4 = w.iW4.h_inv; a.invq = q.iW1.h_inv; a.s4 = 1.0f / w.iW4.h_inv;
+  a.P = P; a.ldp = ldp; a.Nn = q.nq + q.np; a.M = dm.N;
+  a.dead_nt = dead_cols / H; a.dead_mt = a.dead_nt > 0 ? (dead_rows_from + TM - 1) / TM : 0;
+  if (a.Nn % H) { set_error("tc_node_block: %d output columns are not a multiple of hidden_nf", a.Nn); return DSB_ERR_INVALID_ARGUMENT; }
+  const int ntm = (dm.N + TM - 1) / TM, nmp = (ntm + 1) / 2, hw = d->num_sms / 2;
+  const int grid = 2 * (nmp < hw ? nmp : hw);
+  return dispatch_width(H, [&]<int W>() -> int {
+    DSB_CUDA_OK(launch_k_pair(tc_node_block_kernel<W>, grid, TC_THREADS, block_smem_bytes<W>(), s, a));
     return 0;
   });
 }

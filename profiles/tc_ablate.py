@@ -56,6 +56,12 @@ with torch.no_grad():
             ng = max(c[23], 1)
             print(f'   node GEMM CTA0 per launch (cycles): setup {c[16] / ng:7.0f}  epilogue-wait {c[17] / ng:8.0f}  epilogue-work {c[18] / ng:8.0f}  '
                   f'producers {c[19] / ng:8.0f}  body {c[20] / ng:8.0f}  teardown {c[21] / ng:7.0f}  tiles/launch {c[22] / ng:.2f}  (n={ng})')
+        if flags & 512 and c[61]:
+            ni = c[61]
+            for k, name in enumerate(('phase 1 (K=2H)', 'phase 2', 'phase 3 (column tiles)')):
+                o = 48 + 4 * k
+                print(f'   node block, leader MMA thread per item (cycles), {name}: wait-A {c[o] / ni:8.0f}  wait-W {c[o + 1] / ni:8.0f}  wait-peer-W {c[o + 2] / ni:8.0f}  issue {c[o + 3] / ni:8.0f}')
+            print(f'   node block per item: accumulator waits {c[60] / ni:8.0f}  whole loop {c[62] / ni:9.0f}   (items={ni})')
         print(f'flags={flags:2d}  edge_gcl {p["edge_gcl"]["ms"] / 30 * 1e3:8.1f} us/launch   edge_coord {p["edge_coord"]["ms"] / 30 * 1e3:8.1f}'
               f'   node_gemm {p["node_gemm"]["ms"] / 120 * 1e3:7.1f} us/launch', flush=True)
     lib.dsb_debug_set_tc_flags(0)
