@@ -874,6 +874,12 @@ int dsb_set_programmatic_launch(int enable) {
   return old;
 }
 
+int dsb_set_kernel_variants(int variants) {
+  const int old = dsb::g_kernel_variants;
+  if (variants >= 0) dsb::g_kernel_variants = variants & 3;
+  return old;
+}
+
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {
   if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
   if (mode < 0 || mode > 15) { set_error("math mode must be a bitmask in [0,15]"); return DSB_ERR_INVALID_ARGUMENT; }

@@ -145,6 +145,7 @@ void set_error(const char* fmt, ...);
 // prologue (barrier init, TMEM allocation, constant-vector staging) overlap the predecessor's tail.  Both
 // instructions are no-ops for a kernel launched without the attribute.
 extern int g_pdl;
+extern int g_kernel_variants;      // dsb_set_kernel_variants (dsb_tc.cu)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   cudaLaunchConfig_t cfg = {};

@@ -1004,6 +1004,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
 #define DSB_E2_UNROLL 1
 #endif
 constexpr int kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
+#ifndef DSB_RED_PAIR
+#define DSB_RED_PAIR 1          // GCL pass 2: one RED per chunk PAIR of the same receiver
+#endif
 constexpr int EPI_T_STRIDE = 36;          // 16-byte aligned rows: conflict-free row-wise STS.128 and column-wise LDS.32
 constexpr int NSCAL = 3;                   // scalar buffer sets (the j-th tile of a CTA uses set j % NSCAL)
 constexpr int SCAL_WARPS = 2;              // warps 14, 15 of the edge kernels: per-edge scalars one tile ahead of the producers
@@ -1260,6 +1263,49 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         float* G4 = ex->gate4[warp];
         G4[lane] = gate;
         __syncwarp();
+#if DSB_RED_PAIR
+        // lane (rg = lane / 8, cg = lane % 8) owns the chunk PAIR of rows 8 rg .. 8 rg + 7 x columns 4 cg .. 4 cg + 3 of the block:
+        // 8 LDS.128 (one row each; the quarter-warp reads 128 contiguous bytes of a row), the two gate-weighted chunk sums,
+        // and ONE 16-byte RED when both chunks belong to the same receiver (3 of 4 pairs at ~24 edges per receiver; a chunk of
+        // padding has gates 0 and merges with anything), else two: ~35 % fewer atomics to L2 than one per chunk.
+        const int rg = lane >> 3, cg = lane & 7;
+        const float4 ga4 = *reinterpret_cast<const float4*>(G4 + 8 * rg), gb4 = *reinterpret_cast<const float4*>(G4 + 8 * rg + 4);
+        const f32x2 g0 = pk2(ga4.x, ga4.x), g1 = pk2(ga4.y, ga4.y), g2 = pk2(ga4.z, ga4.z), g3 = pk2(ga4.w, ga4.w);
+        const f32x2 g4 = pk2(gb4.x, gb4.x), g5 = pk2(gb4.y, gb4.y), g6 = pk2(gb4.z, gb4.z), g7 = pk2(gb4.w, gb4.w);
+        const int cr0 = ex->row[par][warp * 32 + 8 * rg], cr1 = ex->row[par][warp * 32 + 8 * rg + 4];
+        const bool merge = cr1 < 0 || cr1 == cr0;
+        float* const dstA = a.agg + (size_t)max(cr0, 0) * H + 4 * cg;
+        float* const dstB = a.agg + (size_t)max(cr1, 0) * H + 4 * cg;
+        const float* const tp = T + (8 * rg) * EPI_T_STRIDE + 4 * cg;
+#pragma unroll kE2Unroll
+        for (int cb = 0; cb < ((edbg & 16) ? 0 : TN / 32); ++cb) {
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(T + lane * EPI_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          if (!(edbg & 1024)) {
+            const float4 x0 = *reinterpret_cast<const float4*>(tp), x1 = *reinterpret_cast<const float4*>(tp + EPI_T_STRIDE);
+            const float4 x2 = *reinterpret_cast<const float4*>(tp + 2 * EPI_T_STRIDE), x3 = *reinterpret_cast<const float4*>(tp + 3 * EPI_T_STRIDE);
+            const float4 x4 = *reinterpret_cast<const float4*>(tp + 4 * EPI_T_STRIDE), x5 = *reinterpret_cast<const float4*>(tp + 5 * EPI_T_STRIDE);
+            const float4 x6 = *reinterpret_cast<const float4*>(tp + 6 * EPI_T_STRIDE), x7 = *reinterpret_cast<const float4*>(tp + 7 * EPI_T_STRIDE);
+            f32x2 a01 = add2(fma2(g1, pk2(x1.x, x1.y), mul2(g0, pk2(x0.x, x0.y))), fma2(g3, pk2(x3.x, x3.y), mul2(g2, pk2(x2.x, x2.y))));
+            f32x2 a23 = add2(fma2(g1, pk2(x1.z, x1.w), mul2(g0, pk2(x0.z, x0.w))), fma2(g3, pk2(x3.z, x3.w), mul2(g2, pk2(x2.z, x2.w))));
+            const f32x2 b01 = add2(fma2(g5, pk2(x5.x, x5.y), mul2(g4, pk2(x4.x, x4.y))), fma2(g7, pk2(x7.x, x7.y), mul2(g6, pk2(x6.x, x6.y))));
+            const f32x2 b23 = add2(fma2(g5, pk2(x5.z, x5.w), mul2(g4, pk2(x4.z, x4.w))), fma2(g7, pk2(x7.z, x7.w), mul2(g6, pk2(x6.z, x6.w))));
+            if (merge) { a01 = add2(a01, b01); a23 = add2(a23, b23); }
+            float o0, o1, o2, o3;
+            upk2(a01, o0, o1); upk2(a23, o2, o3);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstA + cb * 32), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
+            if (!merge) {
+              upk2(b01, o0, o1); upk2(b23, o2, o3);
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstB + cb * 32), "f"(o0), "f"(o1), "f"(o2), "f"(o3) : "memory");
+            }
+          }
+          __syncwarp();
+        }
+#else
         const int ck = lane >> 2, cg = lane & 3;
         const float4 gq = *reinterpret_cast<const float4*>(G4 + 4 * ck);         // gates of the chunk's four rows
         const f32x2 g0 = pk2(gq.x, gq.x), g1 = pk2(gq.y, gq.y), g2 = pk2(gq.z, gq.z), g3 = pk2(gq.w, gq.w);
@@ -1291,6 +1337,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
           }
           __syncwarp();
         }
+#endif
       } else {
         // coord: s = phi_m for this edge row; this unit's term of trans (egnn_new.py:100-109)
         const int r = warp * 32 + lane;
@@ -1538,12 +1585,15 @@ template <int H, bool PAIR> static size_t edge_smem_bytes() {
   static_assert(edge_smem_base<H, PAIR>() + sizeof(EdgeExtra<H>) <= 232448, "edge kernel exceeds the 227 KB of shared memory per CTA");
   return edge_smem_base<H, PAIR>() + sizeof(EdgeExtra<H>);
 }
-// The CTA-pair (weight-stationary) form of the 3xFP16 edge kernels is the default; DSB_EDGE_PAIR=0 in the environment selects the
-// single-CTA kernels that stream the weight images (A/B measurements; 3xTF32 always uses them).
-static bool edge_pair_enabled() {
-  static const int v = [] { const char* e = getenv("DSB_EDGE_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
-  return v != 0;
-}
+// Kernel-form selection (dsb_set_kernel_variants): bit 0 = CTA-pair weight-stationary edge kernels, bit 1 = fused node block
+// kernel.  Both default on; 3xTF32 always uses the single-CTA kernels.
+int g_kernel_variants = [] {
+  int v = 3;
+  const char* e = getenv("DSB_EDGE_PAIR"); if (e && e[0] == '0') v &= ~1;
+  e = getenv("DSB_NODE_BLOCK"); if (e && e[0] == '0') v &= ~2;
+  return v;
+}();
+static bool edge_pair_enabled() { return (g_kernel_variants & 1) != 0; }
 
 bool tc_width_supported(int H) { return H == 128 || H == 192 || H == 256; }
 
@@ -1629,8 +1679,7 @@ int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& w
 
 // node_model of GCL `w` followed by the merged first-layer GEMM `q` of the same block (nullptr: none), one launch
 bool tc_node_block_available(int H, bool f16) {
-  static const int on = [] { const char* e = getenv("DSB_NODE_BLOCK"); return (e && e[0] == '0') ? 0 : 1; }();
-  return on && f16 && tc_width_supported(H);
+  return (g_kernel_variants & 2) && f16 && tc_width_supported(H);
 }
 int launch_tc_node_block(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, const GclW& w, const EquivW& q, float* P, int ldp,
                          int dead_rows_from, int dead_cols, cudaStream_t s) {

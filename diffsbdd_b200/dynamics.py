@@ -245,7 +245,8 @@ class EGNNDynamics(nn.Module):
         ws = self._workspace.data_ptr() if self._workspace is not None else 0
         stt = self._status.data_ptr() if self._status is not None else 0
         pdl = int(_native.load().dsb_set_programmatic_launch(-1))
-        return (self._handle_gen, self._handle, self.math_mode, ws, stt, pdl)
+        kv = int(_native.load().dsb_set_kernel_variants(-1))
+        return (self._handle_gen, self._handle, self.math_mode, ws, stt, pdl, kv)
 
     def _scratch(self, device, n_atoms, n_res, n_graphs, ecap) -> torch.Tensor:
         lib = _native.load()

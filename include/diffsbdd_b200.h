@@ -127,6 +127,13 @@ int dsb_dynamics_last_launch_count(const dsb_dynamics* dyn);
  * environment variable DSB_PDL (default on).  No effect on results. */
 int dsb_set_programmatic_launch(int enable);
 
+/* Process-wide selection among equivalent kernel forms of the 3xFP16 path (same results within the parity tolerance).
+ * Bit 0: the edge kernels run as CTA pairs (tcgen05 cta_group::2) with the second-layer weights resident in shared memory
+ * instead of single CTAs that stream them; bit 1: node_model and the merged first-layer GEMM of a block run as one fused
+ * CTA-pair kernel instead of two launches.  variants < 0 = query only.  Returns the previous setting.  Initial value: 3,
+ * minus bit 0 if the environment has DSB_EDGE_PAIR=0, minus bit 1 if DSB_NODE_BLOCK=0. */
+int dsb_set_kernel_variants(int variants);
+
 /* ---- arithmetic path.  mode is a bitmask: 1 = node GEMMs, 2 = edge (GCL) kernel, 4 = coordinate edge kernel run on
  * the tensor pipe (tcgen05.mma, accumulators in TMEM) as 3-product split contractions with fp32 accumulation
  * (x.w ~= x_lo.w_hi + x_hi.w_lo + x_hi.w_hi: fp32-grade accuracy, inside the atol 1e-5 / rtol 1e-4 parity tolerance);

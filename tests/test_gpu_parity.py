@@ -293,3 +293,50 @@ def test_full_batch_oracle_config3():
         ea = assert_close(got[0], want[0], f'full batch ligand out ({mode})')
         er = assert_close(got[1], want[1], f'full batch pocket out ({mode})')
         print(f'configs[2] full batch, {mode}: E={net.last_num_edges} max abs err ligand {ea:.2e} pocket {er:.2e}')
+
+
+def test_single_cta_kernel_forms_still_match():
+    """dsb_set_kernel_variants(0): the single-CTA edge kernels that stream the weight images and the separate node MLP +
+    merged GEMM launches (the forms 3xTF32 always uses) in 3xFP16, against the golden vectors; then back to the default
+    CTA-pair forms, which must agree with them to rounding."""
+    from diffsbdd_b200 import _native
+    lib = _native.load()
+    cfg, sd, inp, want, edges = load_golden('fullatom_b2_n200_l6')
+    net = make_net(cfg, sd)
+    net.math_mode = '3xfp16'
+    old = lib.dsb_set_kernel_variants(0)
+    try:
+        a = run(net, inp)
+        assert_close(a[0], want[0], 'single-CTA forms, ligand out')
+        assert_close(a[1], want[1], 'single-CTA forms, pocket out')
+        for v in (1, 2):
+            lib.dsb_set_kernel_variants(v)
+            b = run(net, inp)
+            assert_close(b[0], want[0], f'kernel variants {v}, ligand out')
+    finally:
+        lib.dsb_set_kernel_variants(old)
+    assert old == 3
+    c = run(net, inp)
+    assert_close(c[0], a[0], 'pair vs single-CTA forms', atol=3e-6, rtol=1e-5)
+
+
+def test_more_row_tiles_than_cta_pairs():
+    """100 graphs x (25 + 175) nodes = 157 row tiles = 79 tile pairs on 74 CTA pairs: five pairs of the fused node block
+    kernel work on a SECOND item (slot hand-over between items, accumulator phase carried across items).  The graphs whose
+    pocket rows fall into those items must come out as when run alone; one of them is checked against the oracle."""
+    cfg = FULLATOM_COND
+    sd = syn.synthetic_state_dict(cfg, 0)
+    B = 100
+    inp = syn.synthetic_denoiser_inputs(cfg, [25] * B, [175] * B, seed=11)
+    net = make_net(cfg, sd)
+    out = run(net, inp)
+    assert torch.count_nonzero(out[1][:, :3]) == 0
+    for g in (0, 93, 97, 99):
+        sa, sr = inp[3] == g, inp[4] == g
+        single = (inp[0][sa], inp[1][sr], inp[2][g:g + 1], torch.zeros(int(sa.sum()), dtype=torch.int64),
+                  torch.zeros(int(sr.sum()), dtype=torch.int64))
+        one = run(net, single)
+        assert_close(one[0], out[0][sa], f'graph {g} alone vs batched (ligand)', atol=3e-6, rtol=1e-5)
+        assert_close(one[1], out[1][sr], f'graph {g} alone vs batched (pocket)', atol=3e-6, rtol=1e-5)
+    want = egnn_oracle.denoiser_forward(cfg, sd, *single)
+    assert_close(one[0], want[0], 'graph 99 vs oracle')
