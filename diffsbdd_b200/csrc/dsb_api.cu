@@ -320,7 +320,7 @@ static Workspace carve(const dsb_config& c, int64_t NL, int64_t NP, int64_t B, i
   ws.xagg = (float4*)take(sizeof(float4) * (N + 1));
   ws.velmean = (float4*)take(sizeof(float4) * (B + 1));
   ws.h = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
-  ws.hT = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
+  ws.hT = (float*)take(sizeof(float) * (size_t)(N + 257) * H);      // also the 3xFP16 operand image of h (whole 128-row tiles, one spare)
   ws.agg = (float*)take(sizeof(float) * (size_t)(N + 1) * H);
   ws.P = (float*)take(sizeof(float) * (size_t)(N + 1) * 6 * H);
   ws.deg = (int32_t*)take(sizeof(int32_t) * (N + 1));
@@ -876,7 +876,7 @@ int dsb_set_programmatic_launch(int enable) {
 
 int dsb_set_kernel_variants(int variants) {
   const int old = dsb::g_kernel_variants;
-  if (variants >= 0) dsb::g_kernel_variants = variants & 3;
+  if (variants >= 0) dsb::g_kernel_variants = variants & 7;
   return old;
 }
 

@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
 // weight columns (B split along N): 32 KB per k-chunk and CTA.
 // Barriers: full_a / epi_done / w_peer live in the leader (cluster rank 0), whose MMA thread issues for both CTAs; the peer's
 // warps arrive through the cluster address space; e0 / e3 / empty_w / acc_full are multicast commits.  A slot is written four
-// times per item (phase-1 chunks 0..3, chunks 4..7, hid, new h): full_a completes four times per item (parity = write & 1).
+// times per item (phase-1 chunks 0..3, chunks 4..7, hid, new h; three without phase 3): full_a completes once per write.
 // A parity wait can only tell "the phase I expect" from "the next one", so every waiter follows its barrier phase by phase:
 // the producers' second write waits for e0 (phase-1 chunk 0..3 read), their first write of the NEXT item for e3 (last
 // phase-3 read), one completion per item each; the epilogue's writes are ordered by acc_full (all MMAs of the phase done).
@@ -616,6 +616,8 @@ struct TcBlockArgs {
   float inv3, inv4, invq, s4;                 // 1 / weight scale per image (powers of two); s4 = 1 / inv4
   float* P; int ldp; int Nn;
   int M; int dead_mt; int dead_nt;            // column tiles < dead_nt are not needed for row tiles >= dead_mt
+  char* himg;                                 // != nullptr: no phase 3; the new h is also written as a 3xFP16 operand image,
+                                              // [row tile][k-chunk][hi | lo: 128 rows x 128 B, SWIZZLE_128B], for tc_pair_gemm_kernel
 };
 struct BlockControl {
   uint64_t full_a[4], e0[4], e3[4];
@@ -745,6 +747,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (u & 1));
         ++u;
+      }
+      if (g.himg) {
+        // ---- phase-2 epilogue without phase 3: new h = acc * inv4 to global memory (in place), as fp32 and as the operand
+        // image the merged GEMM will bulk-copy; aggregate re-armed.  8 lanes cover 128 contiguous bytes of a row (fp32) resp.
+        // 64 bytes of its swizzled image row.
+        mbar_wait(&ctl->acc_full[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tbase + (uint32_t)((u & 1) * ACC_STRIDE);
+        const f32x2 ip = pk2(g.inv4, g.inv4);
+        char* const img = g.himg + (size_t)(2 * item_mp(it) + rank) * (size_t)(NSLOT * SLOT_BYTES);
+#pragma unroll 1
+        for (int cb = 0; cb < H / 32; ++cb) {
+          const int n = cb * 32 + tc4;
+          float v[32];
+          tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + tr;
+            const int row = m0 + warp * 32 + rl;
+            const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+            float4 o;
+            upk2(mul2(pk2(x.x, x.y), ip), o.x, o.y); upk2(mul2(pk2(x.z, x.w), ip), o.z, o.w);
+            if (row < g.M) {
+              *reinterpret_cast<float4*>(g.h + (size_t)row * g.ldh + n) = o;
+              *reinterpret_cast<float4*>(g.agg + (size_t)row * g.ldagg + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            store_piece<true>(img + (size_t)(cb >> 1) * SLOT_BYTES, warp * 32 + rl, cb & 1, lane & 7, o);    // rows beyond M: finite, never used
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (u & 1));
+        ++u;
+        continue;
       }
       // ---- phase-2 epilogue: new h = acc * inv4 (the accumulator started from (h + b4) * s4).  First the phase-3 A operand
       // (fourth write of a slot; phase 3 starts as soon as all four slots are handed over), then the global side: h in place,
@@ -931,22 +972,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
         return tmem + (uint32_t)((u & 1) * ACC_STRIDE);
       };
       auto end_use = [&]() { umma_commit_2cta(&ctl->acc_full[u & 1]); ++u; };
+      const uint32_t wpi = g.himg ? 3u : 4u;       // writes of a slot (= completions of its full_a) per item
       for (int it = 0; it < n_items; ++it) {
+        const uint32_t fa = (uint32_t)it * wpi;     // full_a completions before this item: write k of the item has parity (fa + k) & 1
         ph = 0;
         uint32_t d = begin_use();
-        for (int kc = 0; kc < C1; ++kc) chunk(d, kc % NSLOT, kc < NSLOT ? 0u : 1u, true, kc == 0, kc < NSLOT ? &ctl->e0[kc] : nullptr);     // slot writes 1, 2
+        for (int kc = 0; kc < C1; ++kc) chunk(d, kc % NSLOT, (fa + (kc < NSLOT ? 0u : 1u)) & 1u, true, kc == 0, kc < NSLOT ? &ctl->e0[kc] : nullptr);     // slot writes 1, 2
         end_use();
         ph = 1;
         d = begin_use();
         mbar_wait_cluster(&ctl->pre_done, (uint32_t)it & 1u);          // the accumulator holds the residual in both CTAs
         tc_fence_after();
-        for (int kc = 0; kc < C2; ++kc) chunk(d, kc, 0u, true, false, nullptr);                                // slot write 3 (hid); accumulates onto the residual
+        for (int kc = 0; kc < C2; ++kc) chunk(d, kc, (fa + 2u) & 1u, true, false, g.himg ? &ctl->e3[kc] : nullptr);       // slot write 3 (hid); accumulates onto the residual (no phase 3: last read of the slot)
         end_use();
-        const int nt0 = item_nt0(it);
+        const int nt0 = g.himg ? ntn : item_nt0(it);
         ph = 2;
         for (int nt = nt0; nt < ntn; ++nt) {
           d = begin_use();
-          for (int kc = 0; kc < C2; ++kc) chunk(d, kc, 1u, nt == nt0, kc == 0, nt == ntn - 1 ? &ctl->e3[kc] : nullptr);   // slot write 4 (new h)
+          for (int kc = 0; kc < C2; ++kc) chunk(d, kc, (fa + 3u) & 1u, nt == nt0, kc == 0, nt == ntn - 1 ? &ctl->e3[kc] : nullptr);   // slot write 4 (new h)
           end_use();
         }
       }
@@ -961,7 +1004,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
     } else if (lane == 0) {
       // peer CTA: forward "my weight half of chunk gw has landed" to the leader
       uint32_t total = 0;
-      for (int it = 0; it < n_items; ++it) total += C1 + C2 + (uint32_t)(ntn - item_nt0(it)) * C2;
+      for (int it = 0; it < n_items; ++it) total += C1 + C2 + (g.himg ? 0u : (uint32_t)(ntn - item_nt0(it)) * C2);
       for (uint32_t gw = 0; gw < total; ++gw) {
         mbar_wait(&ctl->full_w[gw & 1], (gw >> 1) & 1);
         mbar_arrive_cluster(l_w_peer + 8u * (gw & 1));
@@ -984,13 +1027,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
       for (int it = 0; it < n_items; ++it) {
         for (int kc = 0; kc < C1; ++kc) load(g.W3hi, g.W3lo, kc);
         for (int kc = 0; kc < C2; ++kc) load(g.W4hi, g.W4lo, kc);
-        for (int nt = item_nt0(it); nt < ntn; ++nt)
+        for (int nt = g.himg ? ntn : item_nt0(it); nt < ntn; ++nt)
           for (int kc = 0; kc < C2; ++kc) load(g.Wqhi + (size_t)nt * C2 * G::B_CHUNK_FLOATS, g.Wqlo + (size_t)nt * C2 * G::B_CHUNK_FLOATS, kc);
       }
     }
     __syncwarp();
   }
   kernel_end();
+}
+
+// =====================================================================================================
+// CTA-pair GEMM from an operand image: C[M][Nn] = h Wq + bq, A = the 3xFP16 image of h written by tc_node_block_kernel.
+// No producer warps: a k-chunk of A (hi | lo, 32 KB: this CTA's 128 rows) and this CTA's half of the weight columns (32 KB)
+// arrive by bulk copy into a 3-deep ring; the leader issues M = 256 MMAs for the pair.  Work items = live (row-tile pair,
+// column tile) combinations dealt round-robin to the 74 pairs: unlike the phase 3 of the fused kernel (one item of 16-24
+// k-chunks per pair, 24 pairs idle, the ligand rows' items 50 % longer than the rest) every pair gets ~3 items of 4 k-chunks.
+// =====================================================================================================
+struct TcPairGemmArgs {
+  const char* himg;                           // [row tile][H/64][hi | lo]
+  const float *Whi, *Wlo; const float* bias; float inv;
+  float* C; int ldc; int M; int Nn; int dead_mt; int dead_nt;
+};
+struct PairGemmControl {
+  uint64_t full[3], peer[3], empty[3];
+  uint64_t acc_full[2], epi_done[2];
+  uint32_t tmem_base, pad;
+};
+constexpr int PG_STAGES = 3;
+template <int H> constexpr size_t pair_gemm_smem_bytes() {
+  return 1024 + (size_t)PG_STAGES * (2 * A_CHUNK_BYTES + (size_t)H * 128) + kControlBytes + sizeof(float) * EPI_WARPS * 32 * GEMM_T_STRIDE;
+}
+constexpr int PG_THREADS = (EPI_WARPS + 2) * 32;      // 4 epilogue warps, MMA warp, bulk-copy warp
+
+template <int H>
+__global__ void __launch_bounds__(PG_THREADS, 1) tc_pair_gemm_kernel(TcPairGemmArgs g) {
+  using G = Geo<H>;
+  constexpr int C2 = H / TKC16;
+  constexpr int SLOT_BYTES = 2 * A_CHUNK_BYTES, HB = (H / 2) * 128, STAGE = SLOT_BYTES + 2 * HB;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+  constexpr int PG_MMA = EPI_WARPS;                // warp PG_MMA + 1 issues the bulk copies
+  extern __shared__ uint8_t smem_raw[];
+  char* const ring = reinterpret_cast<char*>(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  PairGemmControl* ctl = reinterpret_cast<PairGemmControl*>(ring + PG_STAGES * STAGE);
+  float* const Tall = reinterpret_cast<float*>(reinterpret_cast<char*>(ctl) + kControlBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank(), pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int ntm = (g.M + TM - 1) / TM, nmp = (ntm + 1) / 2, ntn = g.Nn / H;
+  // live items: row-tile pairs [0, dmp) x all column tiles, then [dmp, nmp) x column tiles [dead_nt, ntn)
+  const int dmp = g.dead_nt > 0 ? min((g.dead_mt + 1) / 2, nmp) : nmp;
+  const int nA = dmp * ntn, n_live = nA + (nmp - dmp) * (ntn - g.dead_nt);
+  auto item = [&](int t, int& mp, int& nt) {
+    if (t < nA) { mp = t / ntn; nt = t - mp * ntn; }
+    else { const int w = ntn - g.dead_nt, v = t - nA; mp = dmp + v / w; nt = g.dead_nt + (v - (v / w) * w); }
+  };
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < PG_STAGES; ++k) { mbar_init(&ctl->full[k], 1); mbar_init(&ctl->peer[k], 1); mbar_init(&ctl->empty[k], 1); }
+    for (int k = 0; k < 2; ++k) { mbar_init(&ctl->acc_full[k], 1); mbar_init(&ctl->epi_done[k], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == PG_MMA) tmem_alloc2(&ctl->tmem_base, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  pdl_wait();
+  const int n_my = pair < n_live ? (n_live - pair + npairs - 1) / npairs : 0;
+  const uint32_t l_epi_done = leader_addr(&ctl->epi_done[0]), l_peer = leader_addr(&ctl->peer[0]);
+
+  if (warp < EPI_WARPS) {
+    float* T = Tall + warp * (32 * GEMM_T_STRIDE);
+    const int tr = lane >> 3, tc4 = (lane & 7) * 4;
+    const uint32_t tbase = ctl->tmem_base + ((uint32_t)(warp * 32) << 16);
+    const f32x2 ip = pk2(g.inv, g.inv);
+    for (int j = 0; j < n_my; ++j) {
+      int mp, nt;
+      item(pair + j * npairs, mp, nt);
+      const int m0 = (2 * mp + rank) * TM;
+      mbar_wait(&ctl->acc_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tbase + (uint32_t)((j & 1) * ACC_STRIDE);
+#pragma unroll 1
+      for (int cb = 0; cb < H / 32; ++cb) {
+        const int n = nt * H + cb * 32 + tc4;
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        float v[32];
+        tmem_ld32(taddr + cb * 32, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(T + lane * GEMM_T_STRIDE + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const f32x2 b01 = pk2(bias.x, bias.y), b23 = pk2(bias.z, bias.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + tr;
+          const int row = m0 + warp * 32 + rl;
+          const float4 x = *reinterpret_cast<const float4*>(T + rl * GEMM_T_STRIDE + tc4);
+          float4 o;
+          upk2(fma2(pk2(x.x, x.y), ip, b01), o.x, o.y); upk2(fma2(pk2(x.z, x.w), ip, b23), o.z, o.w);
+          if (row < g.M) *reinterpret_cast<float4*>(g.C + (size_t)row * g.ldc + n) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_epi_done + 8u * (uint32_t)(j & 1));
+    }
+  } else if (warp == PG_MMA) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t tmem = ctl->tmem_base;
+      uint32_t gw = 0;
+      for (int j = 0; j < n_my; ++j) {
+        mbar_wait_cluster(&ctl->epi_done[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)((j & 1) * ACC_STRIDE);
+        for (int kc = 0; kc < C2; ++kc, ++gw) {
+          const int s = gw % PG_STAGES;
+          const uint32_t par = (gw / PG_STAGES) & 1;
+          mbar_wait(&ctl->full[s], par);
+          mbar_wait_cluster(&ctl->peer[s], par);
+          tc_fence_after();
+          const uint32_t xhi = smem_u32(ring + (size_t)s * STAGE), xlo = xhi + A_CHUNK_BYTES;
+          const uint32_t whi = xhi + SLOT_BYTES, wlo = whi + HB;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ko = ks * 32;
+            umma_f16_2cta(d, umma_desc_sw128(xlo + ko), umma_desc_sw128(whi + ko), IDESC, (kc == 0 && ks == 0) ? 0u : 1u);
+            umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(wlo + ko), IDESC, 1u);
+            umma_f16_2cta(d, umma_desc_sw128(xhi + ko), umma_desc_sw128(whi + ko), IDESC, 1u);
+          }
+          umma_commit_2cta(&ctl->empty[s]);
+        }
+        umma_commit_2cta(&ctl->acc_full[j & 1]);
+      }
+    } else if (lane == 0) {
+      const uint32_t total = (uint32_t)n_my * C2;        // peer: forward "my stage has landed" to the leader
+      for (uint32_t gw = 0; gw < total; ++gw) {
+        const uint32_t s = gw % PG_STAGES;
+        mbar_wait(&ctl->full[s], (gw / PG_STAGES) & 1);
+        mbar_arrive_cluster(l_peer + 8u * s);
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      uint32_t gw = 0;
+      for (int j = 0; j < n_my; ++j) {
+        int mp, nt;
+        item(pair + j * npairs, mp, nt);
+        const char* a = g.himg + (size_t)(2 * mp + rank) * (size_t)(C2 * SLOT_BYTES);
+        const float* hi = g.Whi + (size_t)nt * C2 * G::B_CHUNK_FLOATS + (size_t)rank * (HB / 4);
+        const float* lo = g.Wlo + (size_t)nt * C2 * G::B_CHUNK_FLOATS + (size_t)rank * (HB / 4);
+        for (int kc = 0; kc < C2; ++kc, ++gw) {
+          const int s = gw % PG_STAGES;
+          mbar_wait(&ctl->empty[s], ((gw / PG_STAGES) & 1) ^ 1);
+          char* dst = ring + (size_t)s * STAGE;
+          mbar_arrive_expect_tx(&ctl->full[s], STAGE);
+          bulk_g2s(dst, a + (size_t)kc * SLOT_BYTES, SLOT_BYTES, &ctl->full[s]);
+          bulk_g2s(dst + SLOT_BYTES, hi + (size_t)kc * G::B_CHUNK_FLOATS, HB, &ctl->full[s]);
+          bulk_g2s(dst + SLOT_BYTES + HB, lo + (size_t)kc * G::B_CHUNK_FLOATS, HB, &ctl->full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == PG_MMA) tmem_dealloc2(ctl->tmem_base, 512);
 }
 
 // =====================================================================================================
@@ -1586,11 +1789,13 @@ template <int H, bool PAIR> static size_t edge_smem_bytes() {
   return edge_smem_base<H, PAIR>() + sizeof(EdgeExtra<H>);
 }
 // Kernel-form selection (dsb_set_kernel_variants): bit 0 = CTA-pair weight-stationary edge kernels, bit 1 = fused node block
-// kernel.  Both default on; 3xTF32 always uses the single-CTA kernels.
+// kernel, bit 2 = its phase 3 as a separate CTA-pair GEMM (off by default: measured equal, one launch more).  3xTF32 always
+// uses the single-CTA kernels.
 int g_kernel_variants = [] {
   int v = 3;
   const char* e = getenv("DSB_EDGE_PAIR"); if (e && e[0] == '0') v &= ~1;
   e = getenv("DSB_NODE_BLOCK"); if (e && e[0] == '0') v &= ~2;
+  e = getenv("DSB_NODE_SPLIT"); if (e && e[0] == '1') v |= 4;
   return v;
 }();
 static bool edge_pair_enabled() { return (g_kernel_variants & 1) != 0; }
@@ -1617,6 +1822,8 @@ int configure_tc_kernels(int H) {
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_gemm_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs));
     static_assert(block_smem_bytes<W>() <= 232448, "node block kernel exceeds shared memory");
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_node_block_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)block_smem_bytes<W>()));
+    static_assert(pair_gemm_smem_bytes<W>() <= 232448, "pair GEMM exceeds shared memory");
+    DSB_CUDA_OK(cudaFuncSetAttribute(tc_pair_gemm_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_gemm_smem_bytes<W>()));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, false, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
     DSB_CUDA_OK(cudaFuncSetAttribute(tc_edge_kernel<false, true, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, es));
@@ -1696,8 +1903,16 @@ int launch_tc_node_block(const dsb_dynamics* d, const Dims& dm, const Workspace&
   if (a.Nn % H) { set_error("tc_node_block: %d output columns are not a multiple of hidden_nf", a.Nn); return DSB_ERR_INVALID_ARGUMENT; }
   const int ntm = (dm.N + TM - 1) / TM, nmp = (ntm + 1) / 2, hw = d->num_sms / 2;
   const int grid = 2 * (nmp < hw ? nmp : hw);
+  const bool split = (g_kernel_variants & 4) != 0;      // phase 3 as a separate, evenly loaded CTA-pair GEMM from the operand image of h
+  a.himg = split ? reinterpret_cast<char*>(ws.hT) : nullptr;
   return dispatch_width(H, [&]<int W>() -> int {
     DSB_CUDA_OK(launch_k_pair(tc_node_block_kernel<W>, grid, TC_THREADS, block_smem_bytes<W>(), s, a));
+    if (split) {
+      TcPairGemmArgs b = {};
+      b.himg = a.himg; b.Whi = a.Wqhi; b.Wlo = a.Wqlo; b.bias = a.bq; b.inv = a.invq;
+      b.C = P; b.ldc = ldp; b.M = dm.N; b.Nn = a.Nn; b.dead_mt = a.dead_mt; b.dead_nt = a.dead_nt;
+      DSB_CUDA_OK(launch_k_pair(tc_pair_gemm_kernel<W>, 2 * hw, PG_THREADS, pair_gemm_smem_bytes<W>(), s, b));
+    }
     return 0;
   });
 }
