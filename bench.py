@@ -508,6 +508,10 @@ def run_b200(args):
             ach_f = alg_flops / (gcl_ms * 1e-3) / 1e12
             smax = (clocks.get('sm_max_mhz') or 1965.0)
             fp32_peak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * 2 * smax * 1e6 / 1e12
+            # the capture's geometry has more edges than this launch: only the 12 B/edge of CSR indices and input distances scale with E
+            if traffic is not None and traffic_edges:
+                traffic = int(traffic - 12 * (traffic_edges - E))
+                traffic_src += f'; captured at E={traffic_edges}, reported for E={E} (-12 B per edge)'
             common = {'kernel': kname, 'avg_launch_ms': gcl_ms, 'edges': E, 'traffic': traffic, 'traffic_edges': traffic_edges,
                       'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': alg_bytes,
                       'algorithmic_flops_per_launch': alg_flops}
