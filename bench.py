@@ -499,7 +499,8 @@ def run_b200(args):
             try:   # DRAM bytes per launch from the committed ncu --set full capture (never measured under the profiler here)
                 with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
                     tj = json.load(f)
-                tr = tj.get(f'{kname}@{args.workload}') or tj.get(kname)
+                # the capture is of the full-atom dimensions (N = 64 x 200 nodes); inpaint runs the same shapes, other workloads have none
+                tr = tj.get(f'{kname}@{args.workload}') or (tj.get(kname) if args.workload in ('fullatom', 'inpaint') else None)
                 if tr:
                     traffic, traffic_src, traffic_edges = tr['dram_bytes_per_launch'], tr['source'], tr.get('edges')
             except Exception:

@@ -828,7 +828,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
       if ((mm & 1) && sub == c.inv_sublayers - 1 && G.iW3.h_hi && G.iW4.h_hi && Qb.iW1.h_hi && !no_fused_mlp && tc_node_block_available(H, f16)) {
         // node_model and the merged first-layer GEMM of this block in one CTA-pair kernel (h converted to operand format once)
         DSB_TRY(launch_tc_node_block(dyn, dm, ws, G, Qb, ws.P, ldP, conditional ? dm.n_coord_rows : 0, conditional ? nrecv : 0, s));
-        launches += 3;
+        launches += 2 + ((g_kernel_variants & 4) ? 1 : 0);      // GCL edge kernel + block kernel (+ the split-off GEMM)
         fused_block = true;
       } else if ((mm & 1) && G.iW3.t_hi && G.iW4.t_hi && !no_fused_mlp) {
         DSB_TRY(launch_tc_node_mlp(dyn, dm, ws, G, f16, status, s));        // both layers in one kernel, hidden stays on chip
@@ -856,7 +856,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     mark(KC_COORD_FINISH);
     DSB_TRY(launch_coord_finish(dyn, dm, ws, xcur, xnext, true, s));
     xcur = xnext;
-    launches += 3;
+    launches += fused_block ? 2 : 3;      // (merged GEMM,) coordinate edge kernel, finish
   }
   mark(KC_POST);
   DSB_TRY(launch_post(dyn, dm, ws, xcur, out_atoms, out_residues, status, s));
