@@ -47,6 +47,10 @@ WORKLOADS = {
     'fullatom': (2, 64, 25, 175, 0.045, (1, 4), 'crossdock_fullatom_cond', True),
     'ca': (1, 32, 25, 40, 0.007, (1, 1), 'crossdock_ca_cond', False),
     'inpaint': (4, 64, 25, 175, 0.045, (1, 4), 'crossdock_fullatom_cond', True),
+    # the other network widths the reference ships (no BASELINE.json entry: index None): same batch shapes, tensor-core kernels
+    # templated on hidden_nf
+    'moad': (None, 64, 25, 175, 0.045, (1, 4), 'moad_fullatom_cond', True),       # hidden_nf 192, edge_embedding_dim 8, cut-offs 4 / 7 A
+    'moad_ca': (None, 32, 25, 40, 0.007, (1, 4), 'moad_ca_cond', False),          # hidden_nf 128, 5 layers, joint_nf 32, cut-offs 8 A
 }
 
 
@@ -79,7 +83,12 @@ def parse_args():
 def workload(args):
     from diffsbdd_b200.config import FULLATOM_COND, CA_COND
     _, _, _, _, density, norm_values, yml, fullatom = WORKLOADS[args.workload]
-    return (FULLATOM_COND if fullatom else CA_COND), density, norm_values, yml
+    cfg = FULLATOM_COND if fullatom else CA_COND
+    if args.workload == 'moad':        # configs/moad_fullatom_cond.yml:30-46
+        cfg = cfg.with_(hidden_nf=192, edge_embedding_dim=8, edge_cutoff_pocket=4.0, edge_cutoff_interaction=7.0)
+    if args.workload == 'moad_ca':     # configs/moad_ca_cond.yml:30-46
+        cfg = cfg.with_(hidden_nf=128, n_layers=5, joint_nf=32, edge_cutoff_pocket=8.0, edge_cutoff_interaction=8.0)
+    return cfg, density, norm_values, yml
 
 
 def denoiser_calls(args):
@@ -95,8 +104,10 @@ def workload_config(args, world=1):
     if args.workload == 'fullatom' and world > 1:
         idx = 3
     name = {1: 'conditional C-alpha model', 2: 'conditional full-atom model', 3: 'conditional full-atom model, batch split over GPUs',
-            4: 'inpainting (ConditionalDDPM.inpaint, fixed-atom mask + resampling), full-atom model'}[idx]
-    cfg = {'workload': (f'BASELINE configs[{idx}]: {name} ({yml}.yml dims), batch {args.batch}/GPU, N_L={args.n_lig}, '
+            4: 'inpainting (ConditionalDDPM.inpaint, fixed-atom mask + resampling), full-atom model',
+            None: 'conditional model of another shipped width'}[idx]
+    head = f'BASELINE configs[{idx}]' if idx is not None else 'not a BASELINE.json configuration'
+    cfg = {'workload': (f'{head}: {name} ({yml}.yml dims), batch {args.batch}/GPU, N_L={args.n_lig}, '
                         f'N_P={args.n_pocket}'),
            'baseline_config_index': idx, 'global_batch': args.batch * world, 'batch_per_gpu': args.batch,
            'n_lig': args.n_lig, 'n_pocket': args.n_pocket, 'pocket_density_per_A3': density,

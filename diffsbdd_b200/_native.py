@@ -32,6 +32,7 @@ class DsbConfig(C.Structure):
         ('norm_constant', C.c_float), ('normalization_factor', C.c_float), ('coords_range', C.c_float),
         ('edge_cutoff_ligand', C.c_float), ('edge_cutoff_pocket', C.c_float),
         ('edge_cutoff_interaction', C.c_float),
+        ('aggregation_mean', C.c_int32),
     ]
 
 

@@ -190,6 +190,7 @@ struct GemmArgs {
   int M; int Nn; int act;                           // act: 0 none, 1 SiLU
   float* Z; int ldz;                                // optional: Z[m][n] = 0 for every output element (re-arms the aggregate)
   int dead_rows_from; int dead_cols;                // output block rows >= dead_rows_from x cols < dead_cols is not needed (skipped)
+  const int32_t* deg2;                              // != nullptr ('mean' aggregation): row m of A2 is divided by max(deg2[m], 1) instead of div2
 };
 int launch_node_gemm(const GemmArgs& a, cudaStream_t s);
 int configure_node_kernels();

@@ -272,7 +272,8 @@ int launch_edges(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, int
 __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restrict__ x_old, float4* __restrict__ x_new,
                                                             float4* __restrict__ xagg, const int32_t* __restrict__ lig_off,
                                                             const int32_t* __restrict__ poc_off, int NL, int n_coord_rows,
-                                                            float norm, int apply_update, float4* __restrict__ cent) {
+                                                            float norm, int apply_update, float4* __restrict__ cent,
+                                                            const int32_t* __restrict__ deg) {
   pdl_trigger();
   pdl_wait();
   const int g = blockIdx.x;
@@ -286,9 +287,10 @@ __global__ void __launch_bounds__(128) coord_finish_kernel(const float4* __restr
       if (i < n_coord_rows) {
         const float4 a = xagg[i];
         xagg[i] = make_float4(0.f, 0.f, 0.f, 0.f);      // re-arm the accumulator for the next block
-        v.x = v.x + __fdiv_rn(a.x, norm);
-        v.y = v.y + __fdiv_rn(a.y, norm);
-        v.z = v.z + __fdiv_rn(a.z, norm);
+        const float dv = deg ? (float)max(deg[i], 1) : norm;          // 'mean' aggregation: the receiver's edge count
+        v.x = v.x + __fdiv_rn(a.x, dv);
+        v.y = v.y + __fdiv_rn(a.y, dv);
+        v.z = v.z + __fdiv_rn(a.z, dv);
       }
       x_new[i] = v;
     }
@@ -317,7 +319,8 @@ int launch_coord_finish(const dsb_dynamics* d, const Dims& dm, const Workspace& 
                         float4* x_new, bool apply_update, cudaStream_t s) {
   if (dm.B == 0) return 0;
   DSB_CUDA_OK(launch_k(coord_finish_kernel, dm.B, 128, 0, s, x_old, x_new, ws.xagg, ws.lig_off, ws.poc_off, dm.NL,
-                       dm.n_coord_rows, d->cfg.normalization_factor, apply_update ? 1 : 0, ws.cent));
+                       dm.n_coord_rows, d->cfg.normalization_factor, apply_update ? 1 : 0, ws.cent,
+                       d->cfg.aggregation_mean ? (const int32_t*)ws.deg : (const int32_t*)nullptr));
   return 0;
 }
 
@@ -502,9 +505,10 @@ __global__ void __launch_bounds__(GTHREADS, 2) node_gemm_kernel(GemmArgs g) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < g.M) {
         v = *reinterpret_cast<const float4*>(A + (size_t)m * lda + kk + a_k4);
-        if (second && g.div2 != 1.0f) {
-          v.x = __fdiv_rn(v.x, g.div2); v.y = __fdiv_rn(v.y, g.div2);
-          v.z = __fdiv_rn(v.z, g.div2); v.w = __fdiv_rn(v.w, g.div2);
+        if (second && (g.div2 != 1.0f || g.deg2)) {
+          const float dv = g.deg2 ? (float)max(g.deg2[m], 1) : g.div2;      // 'mean': the receiver's edge count (egnn_new.py:330-334)
+          v.x = __fdiv_rn(v.x, dv); v.y = __fdiv_rn(v.y, dv);
+          v.z = __fdiv_rn(v.z, dv); v.w = __fdiv_rn(v.w, dv);
         }
       }
       ra[i] = v;

@@ -155,7 +155,7 @@ __device__ __forceinline__ void tma_role(Control* ctl, char* stages, const float
 // =====================================================================================================
 struct TcGemmArgs {
   const float* A1; int lda1; int K1;
-  const float* A2; int lda2; int K2; float div2;
+  const float* A2; int lda2; int K2; float div2; const int32_t* deg2;     // deg2 != nullptr: per-row divisor max(deg2[m], 1) ('mean')
   const float* Bhi; const float* Blo;        // [Nn/256][K/32][8192]
   const float* bias; const float* R; int ldr;
   float* C; int ldc; int M; int Nn; int act;
@@ -316,11 +316,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
       const int kc = q % chunks;
 #pragma unroll
       for (int h = 0; h < HPC; ++h) {
-        const bool second = g.div2 != 1.0f && (kc * HPC + h) * TKC + 4 * pc >= g.K1;      // columns of A2: exact division here,
+        const bool second = (g.div2 != 1.0f || g.deg2) && (kc * HPC + h) * TKC + 4 * pc >= g.K1;      // columns of A2: exact division here,
 #pragma unroll                                                                              // not at load time (keeps the loads in flight)
         for (int i = 0; i < 4; ++i) {
           float4 x = buf[h][i];
-          if (second) { x.x = __fdiv_rn(x.x, g.div2); x.y = __fdiv_rn(x.y, g.div2); x.z = __fdiv_rn(x.z, g.div2); x.w = __fdiv_rn(x.w, g.div2); }
+          if (second) {
+            const int m = tile_m0(q / chunks) + 16 * pw + 4 * sr + i;
+            const float dv = g.deg2 ? (float)max(m < g.M ? g.deg2[m] : 1, 1) : g.div2;
+            x.x = __fdiv_rn(x.x, dv); x.y = __fdiv_rn(x.y, dv); x.z = __fdiv_rn(x.z, dv); x.w = __fdiv_rn(x.w, dv);
+          }
           store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
         }
       }
@@ -377,6 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_gemm_kernel(TcGemmArgs 
 struct TcMlpArgs {
   const float* h; int ldh;                      // A1 of phase 1, residual of phase 2, output (in place)
   const float* agg; int ldagg; float div;       // A2 of phase 1 (exact division), zeroed at the end
+  const int32_t* deg;                           // != nullptr ('mean' aggregation): row m is divided by max(deg[m], 1) instead
   const float* W3hi; const float* W3lo;         // [1][2H/kc][8192] images
   const float* W4hi; const float* W4lo;         // [1][H/kc][8192]
   const float* b3; const float* b4;
@@ -530,7 +535,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_mlp_kernel(TcMlpArgs g)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 x = buf[h][i];
-          if (second) { x.x = __fdiv_rn(x.x, g.div); x.y = __fdiv_rn(x.y, g.div); x.z = __fdiv_rn(x.z, g.div); x.w = __fdiv_rn(x.w, g.div); }
+          if (second) {
+            const int m = (blockIdx.x + it * gridDim.x) * TM + 16 * pw + 4 * sr + i;
+            const float dv = g.deg ? (float)max(m < g.M ? g.deg[m] : 1, 1) : g.div;
+            x.x = __fdiv_rn(x.x, dv); x.y = __fdiv_rn(x.y, dv); x.z = __fdiv_rn(x.z, dv); x.w = __fdiv_rn(x.w, dv);
+          }
           store_piece<F16>(st, 16 * pw + 4 * sr + i, h, pc, x);
         }
       }
@@ -609,7 +618,8 @@ __device__ __forceinline__ float div_by(float x, float d, float r) { const float
 
 struct TcBlockArgs {
   float* h; int ldh;                          // [M][H], updated in place
-  float* agg; int ldagg; float div;           // raw receiver sums: A2 of phase 1 (exact division), zeroed by phase 2
+  float* agg; int ldagg; float div;           // raw receiver sums: A2 of phase 1 (divided by div), zeroed by phase 2
+  const int32_t* deg;                         // != nullptr ('mean' aggregation): row m is divided by max(deg[m], 1) instead
   const float *W3hi, *W3lo, *W4hi, *W4lo;     // node_mlp images
   const float *Wqhi, *Wqlo;                   // merged first-layer images, [Nn/H][H/64][H x 128 B]
   const float *b3, *b4, *bq;
@@ -911,7 +921,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 x = buf[hh][i];
-          if (second) { x.x = div_by(x.x, g.div, rdiv); x.y = div_by(x.y, g.div, rdiv); x.z = div_by(x.z, g.div, rdiv); x.w = div_by(x.w, g.div, rdiv); }
+          if (second) {
+            float dv = g.div, rv = rdiv;
+            if (g.deg) { const int m = (2 * item_mp(it) + rank) * TM + 16 * pw + 4 * sr + i; dv = (float)max(m < g.M ? g.deg[m] : 1, 1); rv = __frcp_rn(dv); }
+            x.x = div_by(x.x, dv, rv); x.y = div_by(x.y, dv, rv); x.z = div_by(x.z, dv, rv); x.w = div_by(x.w, dv, rv);
+          }
           store_piece<true>(st, 16 * pw + 4 * sr + i, hh, pc, x);
         }
       }
@@ -1849,7 +1863,7 @@ int launch_tc_node_gemm(const dsb_dynamics* d, const GemmArgs& g, const TcImage&
     return DSB_ERR_INVALID_ARGUMENT;
   }
   TcGemmArgs a;
-  a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2;
+  a.A1 = g.A1; a.lda1 = g.lda1; a.K1 = g.K1; a.A2 = g.A2; a.lda2 = g.lda2; a.K2 = g.K2; a.div2 = g.div2; a.deg2 = g.deg2;
   const size_t img_off = (size_t)n_tile_off * (K / (f16 ? TKC16 : TKC)) * (size_t)(TN * TKC);     // skip the first n-tiles of the image
   a.Bhi = (f16 ? w.h_hi : w.t_hi) + img_off; a.Blo = (f16 ? w.h_lo : w.t_lo) + img_off;
   a.Z = g.Z; a.ldz = g.ldz;
@@ -1871,6 +1885,7 @@ int launch_tc_node_mlp(const dsb_dynamics* d, const Dims& dm, const Workspace& w
   TcMlpArgs a = {};
   const int H = d->cfg.hidden_nf;
   a.h = ws.h; a.ldh = H; a.agg = ws.agg; a.ldagg = H; a.div = d->cfg.normalization_factor;
+  a.deg = d->cfg.aggregation_mean ? ws.deg : nullptr;
   a.W3hi = f16 ? w.iW3.h_hi : w.iW3.t_hi; a.W3lo = f16 ? w.iW3.h_lo : w.iW3.t_lo;
   a.W4hi = f16 ? w.iW4.h_hi : w.iW4.t_hi; a.W4lo = f16 ? w.iW4.h_lo : w.iW4.t_lo;
   a.b3 = w.b3; a.b4 = w.b4;
@@ -1894,6 +1909,7 @@ int launch_tc_node_block(const dsb_dynamics* d, const Dims& dm, const Workspace&
   const int H = d->cfg.hidden_nf;
   TcBlockArgs a = {};
   a.h = ws.h; a.ldh = H; a.agg = ws.agg; a.ldagg = H; a.div = d->cfg.normalization_factor;
+  a.deg = d->cfg.aggregation_mean ? ws.deg : nullptr;
   a.W3hi = w.iW3.h_hi; a.W3lo = w.iW3.h_lo; a.W4hi = w.iW4.h_hi; a.W4lo = w.iW4.h_lo;
   a.Wqhi = q.iW1.h_hi; a.Wqlo = q.iW1.h_lo;
   a.b3 = w.b3; a.b4 = w.b4; a.bq = q.b1;

@@ -9,7 +9,7 @@ the same ``ValueError("NaN detected in EGNN output")`` convention.  The paramete
 in ``libdiffsbdd_b200.so`` through its C ABI (include/diffsbdd_b200.h) on the caller's CUDA stream.
 
 Out of scope (raises loudly): autograd through the kernels (training), ``mode='gnn_dynamics'``,
-``sin_embedding=True``, ``aggregation_method='mean'`` — none is used by the shipped sampling configs
+``sin_embedding=True`` — neither is used by the shipped sampling configs
 (last row).
 """
 from __future__ import annotations
@@ -94,8 +94,8 @@ class EGNNDynamics(nn.Module):
             raise Exception("Wrong mode %s" % mode)      # dynamics.py:144-145
         if sin_embedding:
             raise NotImplementedError('sin_embedding=True is not built (False in every shipped config)')
-        if aggregation_method != 'sum':
-            raise NotImplementedError("aggregation_method must be 'sum' (every shipped config)")
+        if aggregation_method not in ('sum', 'mean'):
+            raise ValueError("aggregation_method must be 'sum' or 'mean' (egnn_new.py:321-335)")
         if not isinstance(act_fn, nn.SiLU):
             raise NotImplementedError('only SiLU activations are built (lightning_modules.py:143)')
         self.mode = mode
@@ -169,7 +169,8 @@ class EGNNDynamics(nn.Module):
             norm_constant=float(c.norm_constant), normalization_factor=float(c.normalization_factor),
             coords_range=15.0,   # the blocks receive the undivided value (egnn_new.py:197 vs :218)
             edge_cutoff_ligand=neg(c.edge_cutoff_ligand), edge_cutoff_pocket=neg(c.edge_cutoff_pocket),
-            edge_cutoff_interaction=neg(c.edge_cutoff_interaction))
+            edge_cutoff_interaction=neg(c.edge_cutoff_interaction),
+            aggregation_mean=int(c.aggregation_method == 'mean'))
 
     @property
     def math_mode(self) -> int:

@@ -72,6 +72,11 @@ CASES = {
                                                        inv_sublayers=2, reflection_equivariant=True,
                                                        edge_cutoff_pocket=4.0, edge_cutoff_interaction=7.0),
                                         [8, 15], [39, 51], 26, 10, 0.045, 'scalar', (1.0, 4.0)),
+    # aggregation_method='mean' (egnn_new.py:330-334): messages and coordinate updates divided by the receiver's edge count;
+    # conditional H=256 (tensor-core kernels) and joint H=128 with an isolated ligand atom behind a ligand cut-off
+    'mean_h256_l3': (DynamicsConfig(n_layers=3, aggregation_method='mean'), [13, 21], [52, 47], 27, 11, 0.045, None, (1.0, 4.0)),
+    'mean_joint_h128_l2': (DynamicsConfig(n_layers=2, aggregation_method='mean', update_pocket_coords=True, hidden_nf=128,
+                                          joint_nf=32, edge_cutoff_ligand=2.0), [9, 16], [35, 28], 28, 12, 0.045, None, (1.0, 4.0)),
 }
 
 

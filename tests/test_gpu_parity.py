@@ -51,7 +51,7 @@ def test_golden_forward_every_math_mode(case, mode):
 
 
 H256_VARIANTS = ['joint_ca_h256_l6', 'reflect_h256_l3', 'sub2_h256_l2', 'noatt_notanh_h256_l2', 'emb8_h256_l3',
-                 'joint_emb8_sub2_reflect_h256_l2']
+                 'joint_emb8_sub2_reflect_h256_l2', 'mean_h256_l3']
 
 
 @pytest.mark.parametrize('mode', ['fp32', '3xtf32', '3xfp16'])
@@ -59,8 +59,8 @@ H256_VARIANTS = ['joint_ca_h256_l6', 'reflect_h256_l3', 'sub2_h256_l2', 'noatt_n
 def test_golden_h256_variants_every_arithmetic(case, mode):
     """The branches the production config does not take, at hidden_nf=256 so that they run on the tcgen05 kernels too:
     joint mode (all coordinate rows live, velocity mean removal; crossdock_ca_joint.yml dims), reflection-equivariant
-    (one coordinate MLP per tile), two sub-layers, no attention / no tanh, the edge-type table of the producers, and a
-    combination of them.  Goldens come from the unmodified reference (tests/golden/make_golden.py)."""
+    (one coordinate MLP per tile), two sub-layers, no attention / no tanh, the edge-type table of the producers, a
+    combination of them, and aggregation_method='mean'.  Goldens come from the unmodified reference (tests/golden/make_golden.py)."""
     cfg, sd, inp, want, edges = load_golden(case)
     net = make_net(cfg, sd)
     net.math_mode = mode
@@ -70,7 +70,7 @@ def test_golden_h256_variants_every_arithmetic(case, mode):
     assert_close(got_r, want[1], f'{case} mode {mode} pocket out')
 
 
-OTHER_WIDTHS = ['joint_b2_h128_l5', 'moad_emb8_h192_l3', 'reflect_sub2_nocut_l2', 'noatt_notanh_l2']
+OTHER_WIDTHS = ['joint_b2_h128_l5', 'moad_emb8_h192_l3', 'reflect_sub2_nocut_l2', 'noatt_notanh_l2', 'mean_joint_h128_l2']
 
 
 @pytest.mark.parametrize('mode', ['fp32', '3xtf32', '3xfp16'])

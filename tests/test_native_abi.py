@@ -78,8 +78,9 @@ def test_edge_capacity_helper(lib):
 def test_unsupported_reference_options_fail_loudly():
     with pytest.raises(NotImplementedError):
         EGNNDynamics(10, 10, 3, sin_embedding=True)
-    with pytest.raises(NotImplementedError):
-        EGNNDynamics(10, 10, 3, aggregation_method='mean')
+    assert EGNNDynamics(10, 10, 3, aggregation_method='mean').cfg.aggregation_method == 'mean'     # built since round 2
+    with pytest.raises(ValueError):
+        EGNNDynamics(10, 10, 3, aggregation_method='max')
     with pytest.raises(NotImplementedError):
         EGNNDynamics(10, 10, 3, mode='gnn_dynamics')
     with pytest.raises(Exception, match='Wrong mode'):
