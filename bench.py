@@ -442,6 +442,12 @@ def run_b200(args):
     sampler.start()
     ms_total, per_rank_ms = timed(step_device, args.steps)
     clocks = sampler.stop()
+    clocks_by_rank = None
+    if world > 1:      # every rank sampled its own GPU: the per-rank clocks / power / throttle reasons name the limiter of a slow rank
+        allc = [None] * world
+        dist.all_gather_object(allc, {'rank': rank, 'sm_mhz': clocks.get('sm_mhz'), 'power_w_max': clocks.get('power_w_max'),
+                                      'reasons': clocks.get('reasons')})
+        clocks_by_rank = allc
     e_last = dyn.last_num_edges
     atoms_per_step = B * NL * world
     value = atoms_per_step * args.steps / (ms_total / 1e3)
@@ -568,7 +574,7 @@ def run_b200(args):
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfgj,
                 'ms_per_step_by_rank': {'min': min(per_rank_step), 'median': statistics.median(per_rank_step),
                                         'max': max(per_rank_step)},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': gpu_launches,
+                'clocks': clocks, 'clocks_by_rank': clocks_by_rank, 'e2e': e2e, 'gpu_launches': gpu_launches,
                 'launches_per_denoiser_call': launches_fwd, 'math_mode': dyn.math_mode, 'roofline': roof, 'roofline_secondary': roof32,
                 'kernel_ms_per_denoiser_call': kernel_ms, 'cpu_baseline': cpu_base}
         if inpaint:

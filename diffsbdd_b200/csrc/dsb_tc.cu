@@ -1215,10 +1215,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) tc_pair_gemm_kernel(TcPairGemmA
 // =====================================================================================================
 // unroll factors of the epilogue loops (overridable for tuning builds: -DDSB_E1_UNROLL=... etc.)
 #ifndef DSB_E1_UNROLL
-#define DSB_E1_UNROLL 1
+#define DSB_E1_UNROLL 2
 #endif
 #ifndef DSB_E2_UNROLL
-#define DSB_E2_UNROLL 1
+#define DSB_E2_UNROLL 2
 #endif
 constexpr int kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
 #ifndef DSB_RED_PAIR
@@ -1457,7 +1457,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
             a01 = add2(pk2(v[4 * q], v[4 * q + 1]), pk2(bb.x, bb.y));
             a23 = add2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(bb.z, bb.w));
           }
-          silu_pair<(DSB_SILU_PAIR & 2) != 0>(a01, a23);
+          silu_pair<(DSB_SILU_PAIR & 2) != 0, (DSB_SILU_QUAD & 2) != 0>(a01, a23);
           upk2(a01, v[4 * q], v[4 * q + 1]); upk2(a23, v[4 * q + 2], v[4 * q + 3]);
           s01 = fma2(a01, pk2(ww.x, ww.y), s01); s23 = fma2(a23, pk2(ww.z, ww.w), s23);
         }
@@ -1689,7 +1689,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
                 const float4 t4 = *reinterpret_cast<const float4*>(tbm + pty[i] + hf * TKC);
                 u01 = add2(u01, pk2(t4.x, t4.y)); u23 = add2(u23, pk2(t4.z, t4.w));
               }
-              if (!(dbg & 128)) silu_pair<(DSB_SILU_PAIR & 1) != 0>(u01, u23);      // 128: instrumented builds only
+              if (!(dbg & 128)) silu_pair<(DSB_SILU_PAIR & 1) != 0, (DSB_SILU_QUAD & 1) != 0>(u01, u23);      // 128: instrumented builds only
               store_pair<F16>(st + (F16 && (hf & 1) ? (so[i] ^ 64u) : so[i]), u01, u23);
             }
           }
