@@ -1,19 +1,22 @@
 // Tensor-core (tcgen05 / TMEM) kernels of the denoiser: 3-product split contractions (3xFP16 or 3xTF32 operands) with
 // fp32 accumulation in TMEM.
 //
-//   tc_node_gemm_kernel  — C = act([A1 | A2/div] @ W + bias) (+R)        (node GEMMs: egnn_new.py:21-24, factorised W1a/W1b)
-//   tc_edge_kernel<0,.>  — GCL.edge_model + receiver sums                 (egnn_new.py:31-52)
-//   tc_edge_kernel<1,.>  — EquivariantUpdate.coord_model                  (egnn_new.py:96-116)
+//   tc_edge_kernel<0,..>   — GCL.edge_model + receiver sums                 (egnn_new.py:31-52)
+//   tc_edge_kernel<1,..>   — EquivariantUpdate.coord_model                  (egnn_new.py:96-116)
+//                            PAIR = true (3xFP16 default): CTA pairs, tcgen05 cta_group::2, second-layer weights resident
+//   tc_node_block_kernel   — GCL.node_model + the merged first-layer GEMM that consumes the new h, CTA pairs (egnn_new.py:48-58)
+//   tc_pair_gemm_kernel    — that GEMM as a separate CTA-pair kernel fed by an operand image of h (optional split)
+//   tc_node_gemm_kernel    — C = act([A1 | A2/div] @ W + bias) (+R)         (first block's first layer; single-CTA fallback)
+//   tc_node_mlp_kernel     — node_model alone, single CTA                   (3xTF32 / dsb_set_kernel_variants(0))
 //
-// One persistent CTA per SM, warp-specialised (see dsb_tc.cuh):
-//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = one tile row), bias/SiLU/gate, 4-row chunk sums, RED/STG
+// One persistent CTA per SM, warp-specialised (see dsb_tc.cuh); the roles of the edge kernels:
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (thread = one tile row), bias/SiLU/gate, chunk sums, RED
 //   warps 4-11  producers: build the A operand chunk (gather Pa[row]+Pb[col]+radial terms, SiLU, hi/lo split) straight
-//               into 128B-swizzled shared memory; fence.proxy.async; arrive on full_x
-//   warp 12     MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 split terms) per K-chunk
-//   warp 13     bulk-copy issuer: cp.async.bulk of the pre-split, pre-swizzled weight chunk images (hi, lo) -> full_w
-//   warps 14-15 (edge kernels only) scalar warps: per-edge indices, distances and directions one tile ahead
-// Two shared-memory stages (96 KB each) and two 256-column TMEM accumulators: the epilogue of tile t overlaps the
-// main loop of tile t+1.
+//               into 128B-swizzled shared memory; fence.proxy.async; arrive on full_x (of the pair's leader CTA)
+//   warp 12     MMA issuer: one thread (of the leader CTA) issues 12 tcgen05.mma (4 k-steps x 3 split terms) per K-chunk
+//   warp 13     bulk-copy issuer: cp.async.bulk of the pre-split, pre-swizzled weight images (once per launch when resident)
+//   warps 14-15 scalar warps: per-edge indices, distances and directions one tile ahead
+// Two operand stages and two 256-column TMEM accumulators: the epilogue of tile t overlaps the main loop of tile t+1.
 #include <cstdlib>
 
 #include "dsb_tc.cuh"
