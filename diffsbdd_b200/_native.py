@@ -33,6 +33,7 @@ class DsbConfig(C.Structure):
         ('edge_cutoff_ligand', C.c_float), ('edge_cutoff_pocket', C.c_float),
         ('edge_cutoff_interaction', C.c_float),
         ('aggregation_mean', C.c_int32),
+        ('sin_embedding', C.c_int32),
     ]
 
 

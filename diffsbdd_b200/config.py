@@ -43,8 +43,9 @@ class DynamicsConfig:
 
     @property
     def edge_feat_nf(self) -> int:
-        """Width of the per-edge attribute vector (reference egnn_new.py:203-210)."""
-        return 2 + (self.edge_embedding_dim or 0)
+        """Width of the per-edge attribute vector (reference egnn_new.py:203-210): current and input-geometry d^2 (or their
+        sinusoidal embeddings, 2 x 12 features, egnn_new.py:282-293) + the edge-type embedding."""
+        return (24 if self.sin_embedding else 2) + (self.edge_embedding_dim or 0)
 
 
 # BASELINE.json configs (dims from configs/crossdock_{fullatom,ca}_cond.yml:30-52,

@@ -48,7 +48,7 @@ static int validate(const dsb_config* c) {
 static std::vector<ParamInfo> param_table(const dsb_config& c) {
   std::vector<ParamInfo> v;
   const int A = c.atom_nf, R = c.residue_nf, J = c.joint_nf, H = c.hidden_nf;
-  const int Din = J + (c.condition_time ? 1 : 0), F = 2 + c.edge_embedding_dim;
+  const int Din = J + (c.condition_time ? 1 : 0), F = (c.sin_embedding ? 24 : 2) + c.edge_embedding_dim;      // egnn_new.py:203-210
   auto lin = [&](const std::string& p, int out_f, int in_f, bool bias = true) {
     v.push_back({p + ".weight", (int64_t)out_f * in_f, out_f, in_f});
     if (bias) v.push_back({p + ".bias", out_f, out_f, 1});
@@ -178,7 +178,8 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
                         size_t* floats_out) {
   const dsb_config& c = d->cfg;
   const int H = c.hidden_nf, J = c.joint_nf, Din = J + (c.condition_time ? 1 : 0), De = c.edge_embedding_dim;
-  const int F = 2 + De, ld1 = 2 * H + F;
+  const int NS = c.sin_embedding ? 12 : 1;         // radial features per distance: d^2, or its 12 sinusoids (egnn_new.py:282-293)
+  const int F = 2 * NS + De, ld1 = 2 * H + F;
   std::map<std::string, int> index;
   for (size_t i = 0; i < tab.size(); ++i) index[tab[i].name] = (int)i;
   auto P = [&](const std::string& n) -> const float* { return dry ? nullptr : params[index.at(n)]; };
@@ -214,11 +215,11 @@ static int pack_weights(dsb_dynamics* d, const float* const* params, const std::
     pk.T(W1, ld1, 0, H, H, W1dst, ldd, dcol_recv);     // receiver part  (h[row], egnn_new.py:35/99)
     pk.T(W1, ld1, H, H, H, W1dst, ldd, dcol_send);     // sender part    (h[col])
     if (!dry) pack_copy_kernel<<<(H + 255) / 256, 256>>>(b1dst + dcol_recv, P(pre + ".bias"), H);
-    float* r = pk.alloc(H); pk.T(W1, ld1, 2 * H, H, 1, r, H, 0); *wr = r;
-    float* r0 = pk.alloc(H); pk.T(W1, ld1, 2 * H + 1, H, 1, r0, H, 0); *wr0 = r0;
+    float* r = pk.alloc((size_t)NS * H); pk.T(W1, ld1, 2 * H, H, NS, r, H, 0); *wr = r;                 // [NS][H]: current geometry
+    float* r0 = pk.alloc((size_t)NS * H); pk.T(W1, ld1, 2 * H + NS, H, NS, r0, H, 0); *wr0 = r0;      // [NS][H]: input geometry
     if (De > 0) {
       float* t = pk.alloc((size_t)3 * H);
-      if (!dry) pack_tb_kernel<<<(3 * H + 255) / 256, 256>>>(t, W1, ld1, 2 * H + 2, emb, De, H);
+      if (!dry) pack_tb_kernel<<<(3 * H + 255) / 256, 256>>>(t, W1, ld1, 2 * H + 2 * NS, emb, De, H);
       *tb = t;
     } else {
       *tb = nullptr;
@@ -786,7 +787,7 @@ int dsb_dynamics_forward(dsb_dynamics* dyn, const float* xh_atoms, const float* 
     if (cls >= 0 && dyn->prof_n < kMaxProfEvents) { cudaEventRecord(dyn->prof_ev[2 * dyn->prof_n], s); cur_cls = cls; }
   };
 #define DSB_TRY(expr) do { if (int e_ = (expr)) return e_; } while (0)
-  const int mm = tc_width_supported(H) ? dyn->math_mode : 0;
+  const int mm = (tc_width_supported(H) && !c.sin_embedding) ? dyn->math_mode : 0;      // sin_embedding: fp32 FFMA kernels only
   const bool f16 = (mm & 8) != 0;
   auto gemm = [&](const GemmArgs& ga, const TcImage& img, int n_tile_off = 0) -> int {
     return ((mm & 1) && img.t_hi) ? launch_tc_node_gemm(dyn, ga, img, n_tile_off, f16, status, s) : launch_node_gemm(ga, s);
@@ -884,6 +885,7 @@ int dsb_set_kernel_variants(int variants) {
 int dsb_dynamics_set_math_mode(dsb_dynamics* dyn, int mode) {
   if (!dyn) { set_error("null handle"); return DSB_ERR_INVALID_ARGUMENT; }
   if (mode < 0 || mode > 15) { set_error("math mode must be a bitmask in [0,15]"); return DSB_ERR_INVALID_ARGUMENT; }
+  if (mode != 0 && dyn->cfg.sin_embedding) { set_error("sin_embedding is built in the fp32 FFMA kernels only (math mode 0)"); return DSB_ERR_UNSUPPORTED_CONFIG; }
   if (mode != 0 && !tc_width_supported(dyn->cfg.hidden_nf)) { set_error("the tcgen05 kernels are built for hidden_nf 128, 192 and 256 only"); return DSB_ERR_UNSUPPORTED_CONFIG; }
   dyn->math_mode = mode;
   return 0;

@@ -36,14 +36,19 @@ struct EdgeSmem {
 
 // ---- shared main loop --------------------------------------------------------------------------------
 // acc[i][q*4+j] accumulates row (ty*8+i), column (64*q + tx*4 + j) of  X @ W2.
-template <int H>
+template <int H, bool SIN>
 __device__ __forceinline__ void edge_mlp_mainloop(
     float (&acc)[8][H / 16], float* __restrict__ Xs, float* __restrict__ Ws,
     const float* __restrict__ P, int ldp, int offA, int offB,
     const float* __restrict__ s_wr, const float* __restrict__ s_wr0, const float* __restrict__ s_tb,
     const int* __restrict__ s_row, const int* __restrict__ s_col, const float* __restrict__ s_d2,
     const float* __restrict__ s_d0, const int* __restrict__ s_type,
-    const float* __restrict__ W2) {
+    const float* __restrict__ W2,
+    const float* __restrict__ g_wr = nullptr, const float* __restrict__ g_wr0 = nullptr) {
+  // g_wr != nullptr: sin_embedding (egnn_new.py:282-293).  The two distances enter the first layer as 12 sinusoids each:
+  // [sin(f_k d) | cos(f_k d)], f_k = 2 pi 4^k / 15, d = sqrt(d^2 + 1e-8); g_wr / g_wr0 = their [12][H] weight rows (global
+  // memory, L1-resident).  24 FMAs per first-layer value instead of 2: the flag is unused by every shipped config and is
+  // built for completeness, not speed.
   constexpr int NQ = H / 64;
   constexpr int NCH = H / EKC;
   const int tid = threadIdx.x;
@@ -54,6 +59,16 @@ __device__ __forceinline__ void edge_mlp_mainloop(
   const int pcol = s_col[pr];
   const float pd2 = s_d2[pr], pd0 = s_d0[pr];
   const int ptype = s_type ? s_type[pr] : 0;
+  float emb[SIN ? 24 : 1];
+  if constexpr (SIN) {
+    const float dc = sqrtf(pd2 + 1e-8f), di = sqrtf(pd0 + 1e-8f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float f = __fdiv_rn(6.2831853071795864769f * (float)(1 << (2 * k)), 15.0f);      // torch: fp32(2 pi) * 4^k / 15
+      emb[k] = sinf(dc * f); emb[6 + k] = cosf(dc * f);
+      emb[12 + k] = sinf(di * f); emb[18 + k] = cosf(di * f);
+    }
+  }
   const float* Pa = P + (size_t)prow * ldp + offA;
   const float* Pb = P + (size_t)pcol * ldp + offB;
 
@@ -80,8 +95,17 @@ __device__ __forceinline__ void edge_mlp_mainloop(
       float v[4] = {ga[q].x + gb[q].x, ga[q].y + gb[q].y, ga[q].z + gb[q].z, ga[q].w + gb[q].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float u = fmaf(pd2, s_wr[k0 + j], v[j]);
-        u = fmaf(pd0, s_wr0[k0 + j], u);
+        float u;
+        if constexpr (SIN) {
+          u = v[j];
+#pragma unroll
+          for (int f = 0; f < 12; ++f) u = fmaf(emb[f], __ldg(g_wr + f * H + k0 + j), u);
+#pragma unroll
+          for (int f = 0; f < 12; ++f) u = fmaf(emb[12 + f], __ldg(g_wr0 + f * H + k0 + j), u);
+        } else {
+          u = fmaf(pd2, s_wr[k0 + j], v[j]);
+          u = fmaf(pd0, s_wr0[k0 + j], u);
+        }
         if (s_tb) u += s_tb[ptype * H + k0 + j];
         X[(kl + j) * EXS + pr] = silu_f(u);
       }
@@ -144,7 +168,7 @@ struct EdgeGclArgs {
   float* agg;                        // [N][H], zero on entry; receives raw sums
 };
 
-template <int H>
+template <int H, bool SIN>
 __global__ void __launch_bounds__(ETHREADS, 1) edge_gcl_kernel(EdgeGclArgs a) {
   extern __shared__ __align__(16) float smem[];
   using S = EdgeSmem<H>;
@@ -190,8 +214,8 @@ __global__ void __launch_bounds__(ETHREADS, 1) edge_gcl_kernel(EdgeGclArgs a) {
     __syncthreads();
 
     float acc[8][H / 16];
-    edge_mlp_mainloop<H>(acc, Xs, Ws, a.P, a.ldp, 0, H, s_wr, s_wr0, has_tb ? s_tb : nullptr,
-                         s_row, s_col, s_d2, s_d0, has_tb ? s_type : nullptr, a.w.W2);
+    edge_mlp_mainloop<H, SIN>(acc, Xs, Ws, a.P, a.ldp, 0, H, s_wr, s_wr0, has_tb ? s_tb : nullptr,
+                              s_row, s_col, s_d2, s_d0, has_tb ? s_type : nullptr, a.w.W2, a.w.wr, a.w.wr0);
 
     // ---- epilogue: m = SiLU(acc + b2); e = m * sigmoid(wa.m + ba)  (egnn_new.py:36-40)
 #pragma unroll
@@ -259,7 +283,7 @@ struct EdgeCoordArgs {
   float4* xagg;                      // [N], zero on entry; receives raw sums of trans
 };
 
-template <int H>
+template <int H, bool SIN>
 __global__ void __launch_bounds__(ETHREADS, 1) edge_coord_kernel(EdgeCoordArgs a) {
   extern __shared__ __align__(16) float smem[];
   using S = EdgeSmem<H>;
@@ -322,9 +346,9 @@ __global__ void __launch_bounds__(ETHREADS, 1) edge_coord_kernel(EdgeCoordArgs a
     for (int m = 0; m < a.nm; ++m) {
       float acc[8][H / 16];
       const float* v = s_vec + m * 6 * H;
-      edge_mlp_mainloop<H>(acc, Xs, Ws, a.P, a.ldp, m * H, a.nm * H + m * H, v, v + H,
-                           has_tb ? v + 3 * H : nullptr, s_row, s_col, s_d2, s_d0,
-                           has_tb ? s_type : nullptr, a.w.W2[m]);
+      edge_mlp_mainloop<H, SIN>(acc, Xs, Ws, a.P, a.ldp, m * H, a.nm * H + m * H, v, v + H,
+                                has_tb ? v + 3 * H : nullptr, s_row, s_col, s_d2, s_d0,
+                                has_tb ? s_type : nullptr, a.w.W2[m], a.w.wr[m], a.w.wr0[m]);
       const float* b2 = v + 2 * H;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {   // phi = w3 . SiLU(acc + b2)   (egnn_new.py:83-85, bias-free last layer)
@@ -385,8 +409,10 @@ template <int H> static size_t coord_smem_bytes() {
 }
 
 template <int H> static int configure_h() {
-  DSB_CUDA_OK(cudaFuncSetAttribute(edge_gcl_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gcl_smem_bytes<H>()));
-  DSB_CUDA_OK(cudaFuncSetAttribute(edge_coord_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coord_smem_bytes<H>()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_gcl_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gcl_smem_bytes<H>()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_coord_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coord_smem_bytes<H>()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_gcl_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gcl_smem_bytes<H>()));
+  DSB_CUDA_OK(cudaFuncSetAttribute(edge_coord_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coord_smem_bytes<H>()));
   return 0;
 }
 
@@ -407,11 +433,12 @@ int launch_edge_gcl(const dsb_dynamics* d, const Dims& dm, const Workspace& ws, 
   a.P = pv.P; a.ldp = pv.ldp; a.x = x; a.row_ptr = ws.row_ptr; a.N = dm.N;
   a.erow = ws.erow; a.ecol = ws.ecol; a.ed0 = ws.ed0; a.NL = dm.NL; a.w = w; a.agg = ws.agg;
   const int grid = d->num_sms;
+  const bool sin = d->cfg.sin_embedding != 0;
   switch (H) {
-    case 64: edge_gcl_kernel<64><<<grid, ETHREADS, gcl_smem_bytes<64>(), s>>>(a); break;
-    case 128: edge_gcl_kernel<128><<<grid, ETHREADS, gcl_smem_bytes<128>(), s>>>(a); break;
-    case 192: edge_gcl_kernel<192><<<grid, ETHREADS, gcl_smem_bytes<192>(), s>>>(a); break;
-    case 256: edge_gcl_kernel<256><<<grid, ETHREADS, gcl_smem_bytes<256>(), s>>>(a); break;
+    case 64: if (sin) edge_gcl_kernel<64, true><<<grid, ETHREADS, gcl_smem_bytes<64>(), s>>>(a); else edge_gcl_kernel<64, false><<<grid, ETHREADS, gcl_smem_bytes<64>(), s>>>(a); break;
+    case 128: if (sin) edge_gcl_kernel<128, true><<<grid, ETHREADS, gcl_smem_bytes<128>(), s>>>(a); else edge_gcl_kernel<128, false><<<grid, ETHREADS, gcl_smem_bytes<128>(), s>>>(a); break;
+    case 192: if (sin) edge_gcl_kernel<192, true><<<grid, ETHREADS, gcl_smem_bytes<192>(), s>>>(a); else edge_gcl_kernel<192, false><<<grid, ETHREADS, gcl_smem_bytes<192>(), s>>>(a); break;
+    case 256: if (sin) edge_gcl_kernel<256, true><<<grid, ETHREADS, gcl_smem_bytes<256>(), s>>>(a); else edge_gcl_kernel<256, false><<<grid, ETHREADS, gcl_smem_bytes<256>(), s>>>(a); break;
     default: return DSB_ERR_UNSUPPORTED_CONFIG;
   }
   DSB_CUDA_OK(cudaGetLastError());
@@ -430,11 +457,12 @@ int launch_edge_coord(const dsb_dynamics* d, const Dims& dm, const Workspace& ws
   a.norm_constant = c.norm_constant; a.coords_range = c.coords_range; a.use_tanh = c.tanh;
   a.xagg = ws.xagg;
   const int grid = d->num_sms;
+  const bool sin = c.sin_embedding != 0;
   switch (H) {
-    case 64: edge_coord_kernel<64><<<grid, ETHREADS, coord_smem_bytes<64>(), s>>>(a); break;
-    case 128: edge_coord_kernel<128><<<grid, ETHREADS, coord_smem_bytes<128>(), s>>>(a); break;
-    case 192: edge_coord_kernel<192><<<grid, ETHREADS, coord_smem_bytes<192>(), s>>>(a); break;
-    case 256: edge_coord_kernel<256><<<grid, ETHREADS, coord_smem_bytes<256>(), s>>>(a); break;
+    case 64: if (sin) edge_coord_kernel<64, true><<<grid, ETHREADS, coord_smem_bytes<64>(), s>>>(a); else edge_coord_kernel<64, false><<<grid, ETHREADS, coord_smem_bytes<64>(), s>>>(a); break;
+    case 128: if (sin) edge_coord_kernel<128, true><<<grid, ETHREADS, coord_smem_bytes<128>(), s>>>(a); else edge_coord_kernel<128, false><<<grid, ETHREADS, coord_smem_bytes<128>(), s>>>(a); break;
+    case 192: if (sin) edge_coord_kernel<192, true><<<grid, ETHREADS, coord_smem_bytes<192>(), s>>>(a); else edge_coord_kernel<192, false><<<grid, ETHREADS, coord_smem_bytes<192>(), s>>>(a); break;
+    case 256: if (sin) edge_coord_kernel<256, true><<<grid, ETHREADS, coord_smem_bytes<256>(), s>>>(a); else edge_coord_kernel<256, false><<<grid, ETHREADS, coord_smem_bytes<256>(), s>>>(a); break;
     default: return DSB_ERR_UNSUPPORTED_CONFIG;
   }
   DSB_CUDA_OK(cudaGetLastError());

@@ -8,8 +8,8 @@ the same ``ValueError("NaN detected in EGNN output")`` convention.  The paramete
 ``nn.Parameter`` leaves in a module tree that reproduces the reference key names; all arithmetic happens
 in ``libdiffsbdd_b200.so`` through its C ABI (include/diffsbdd_b200.h) on the caller's CUDA stream.
 
-Out of scope (raises loudly): autograd through the kernels (training), ``mode='gnn_dynamics'``,
-``sin_embedding=True`` — neither is used by the shipped sampling configs
+Out of scope (raises loudly): autograd through the kernels (training), ``mode='gnn_dynamics'`` — not used by the
+shipped sampling configs
 (last row).
 """
 from __future__ import annotations
@@ -92,8 +92,6 @@ class EGNNDynamics(nn.Module):
             if mode == 'gnn_dynamics':
                 raise NotImplementedError("mode='gnn_dynamics' is not built (unused by every shipped config)")
             raise Exception("Wrong mode %s" % mode)      # dynamics.py:144-145
-        if sin_embedding:
-            raise NotImplementedError('sin_embedding=True is not built (False in every shipped config)')
         if aggregation_method not in ('sum', 'mean'):
             raise ValueError("aggregation_method must be 'sum' or 'mean' (egnn_new.py:321-335)")
         if not isinstance(act_fn, nn.SiLU):
@@ -111,7 +109,7 @@ class EGNNDynamics(nn.Module):
         self.cfg = DynamicsConfig(
             atom_nf=atom_nf, residue_nf=residue_nf, n_dims=n_dims, joint_nf=joint_nf, hidden_nf=hidden_nf,
             n_layers=n_layers, attention=bool(attention), condition_time=bool(condition_time), tanh=bool(tanh),
-            mode=mode, norm_constant=norm_constant, inv_sublayers=inv_sublayers, sin_embedding=False,
+            mode=mode, norm_constant=norm_constant, inv_sublayers=inv_sublayers, sin_embedding=bool(sin_embedding),
             normalization_factor=normalization_factor, aggregation_method=aggregation_method,
             update_pocket_coords=bool(update_pocket_coords), edge_cutoff_ligand=edge_cutoff_ligand,
             edge_cutoff_pocket=edge_cutoff_pocket, edge_cutoff_interaction=edge_cutoff_interaction,
@@ -170,13 +168,14 @@ class EGNNDynamics(nn.Module):
             coords_range=15.0,   # the blocks receive the undivided value (egnn_new.py:197 vs :218)
             edge_cutoff_ligand=neg(c.edge_cutoff_ligand), edge_cutoff_pocket=neg(c.edge_cutoff_pocket),
             edge_cutoff_interaction=neg(c.edge_cutoff_interaction),
-            aggregation_mean=int(c.aggregation_method == 'mean'))
+            aggregation_mean=int(c.aggregation_method == 'mean'), sin_embedding=int(c.sin_embedding))
 
     @property
     def math_mode(self) -> int:
         m = self._math_mode
         if m in ('auto', None):
-            return 15 if self.cfg.hidden_nf in (128, 192, 256) else 0
+            # sin_embedding (unused by every shipped config) is built in the fp32 FFMA kernels only
+            return 15 if self.cfg.hidden_nf in (128, 192, 256) and not self.cfg.sin_embedding else 0
         if m == 'fp32':
             return 0
         if m == '3xtf32':

@@ -27,7 +27,7 @@ extern "C" {
 typedef enum {
   DSB_OK = 0,
   DSB_ERR_INVALID_ARGUMENT = -1,
-  DSB_ERR_UNSUPPORTED_CONFIG = -2, /* sin_embedding, mode 'gnn_dynamics', H not in {64..256 step 64} */
+  DSB_ERR_UNSUPPORTED_CONFIG = -2, /* mode 'gnn_dynamics', H not in {64..256 step 64}, tensor-core math modes with sin_embedding */
   DSB_ERR_CUDA = -3,
   DSB_ERR_WORKSPACE_TOO_SMALL = -4
 } dsb_status;
@@ -56,6 +56,8 @@ typedef struct {
   float edge_cutoff_interaction;
   int32_t aggregation_mean;      /* bool: aggregation_method == 'mean' (egnn_new.py:330-334: sums divided by the receiver's edge count,
                                   * 1 for a receiver without edges) instead of 'sum' (divided by normalization_factor) */
+  int32_t sin_embedding;         /* bool: the two squared distances of an edge enter the MLPs as 2 x 12 sinusoidal features
+                                  * (egnn_new.py:282-293); fp32 FFMA kernels only (math mode 0) */
 } dsb_config;
 
 typedef struct dsb_dynamics dsb_dynamics; /* opaque: packed weights for one EGNNDynamics module */

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import math
+
 import torch
 import torch.nn.functional as F
 
@@ -123,11 +125,22 @@ def equivariant_update(sd, prefix, cfg, h, x, row, col, direction, cross, edge_a
     return x + agg
 
 
+def sin_embedding(d2):
+    """egnn_new.py:282-293 (``SinusoidsEmbeddingNew``, max_res=15, min_res=15/2000, div_factor=4): 6 frequencies
+    2*pi*4^k/15, features [sin(f_k d) | cos(f_k d)] of d = sqrt(d^2 + 1e-8)."""
+    n = int(math.log(15. / (15. / 2000.), 4)) + 1
+    freq = 2 * math.pi * 4 ** torch.arange(n) / 15.
+    emb = torch.sqrt(d2 + 1e-8) * freq[None, :].to(d2.device)
+    return torch.cat((emb.sin(), emb.cos()), dim=-1)
+
+
 def egnn_stack(sd, cfg, h, x, edges, update_coords_mask, batch_mask, edge_type_emb):
     """egnn_new.py:225-244 with the block body :163-184. ``coords_range`` passed to the blocks is
     the undivided 15.0 (egnn_new.py:197 computes /n_layers but :218 passes the raw value)."""
     row, col = edges[0], edges[1]
     d2_in, _ = radial_and_direction(x, row, col, 1)          # egnn_new.py:228 (default norm_constant)
+    if cfg.sin_embedding:
+        d2_in = sin_embedding(d2_in)                         # egnn_new.py:229-230
     edge_feat = d2_in if edge_type_emb is None else torch.cat([d2_in, edge_type_emb], dim=1)
     h = _linear(sd, 'egnn.embedding', h)
     coords_range = 15.0
@@ -136,6 +149,8 @@ def egnn_stack(sd, cfg, h, x, edges, update_coords_mask, batch_mask, edge_type_e
         d2, direction = radial_and_direction(x, row, col, cfg.norm_constant)
         cross = None if cfg.reflection_equivariant else \
             cross_direction(x, row, col, batch_mask, cfg.norm_constant)
+        if cfg.sin_embedding:
+            d2 = sin_embedding(d2)                           # egnn_new.py:173-174
         edge_attr = torch.cat([d2, edge_feat], dim=1)
         for s in range(cfg.inv_sublayers):
             h = gcl(sd, f'{b}.gcl_{s}', cfg, h, row, col, edge_attr)
@@ -154,8 +169,8 @@ def denoiser_forward(cfg, state_dict: Dict[str, torch.Tensor], xh_atoms, xh_resi
     raises ``ValueError('NaN detected in EGNN output')`` like dynamics.py:155-159.  ``device='cuda'`` runs the very same
     ATen op sequence on the GPU: that is bench.py's ``--impl reference-gpu`` arm ("the reference's own PyTorch graph on
     the B200"), never a checker and never the product path."""
-    if cfg.mode != 'egnn_dynamics' or cfg.sin_embedding:
-        raise NotImplementedError('oracle covers mode=egnn_dynamics, sin_embedding=False')
+    if cfg.mode != 'egnn_dynamics':
+        raise NotImplementedError('oracle covers mode=egnn_dynamics')
     sd = {k: v.detach().to(device, dtype) for k, v in state_dict.items()}
     xh_atoms = xh_atoms.detach().to(device, dtype)
     xh_residues = xh_residues.detach().to(device, dtype)

@@ -77,6 +77,11 @@ CASES = {
     'mean_h256_l3': (DynamicsConfig(n_layers=3, aggregation_method='mean'), [13, 21], [52, 47], 27, 11, 0.045, None, (1.0, 4.0)),
     'mean_joint_h128_l2': (DynamicsConfig(n_layers=2, aggregation_method='mean', update_pocket_coords=True, hidden_nf=128,
                                           joint_nf=32, edge_cutoff_ligand=2.0), [9, 16], [35, 28], 28, 12, 0.045, None, (1.0, 4.0)),
+    # sin_embedding=True (egnn_new.py:282-293): 2 x 12 sinusoidal distance features instead of the two squared distances;
+    # with the edge-type embedding behind them, H=256 and H=128
+    'sin_h256_l2': (DynamicsConfig(n_layers=2, sin_embedding=True), [12, 9], [40, 33], 29, 13, 0.045, None, (1.0, 4.0)),
+    'sin_emb8_joint_h128_l2': (DynamicsConfig(n_layers=2, sin_embedding=True, edge_embedding_dim=8, update_pocket_coords=True,
+                                              hidden_nf=128, joint_nf=32), [10, 7], [30, 36], 30, 14, 0.045, None, (1.0, 4.0)),
 }
 
 

@@ -340,3 +340,20 @@ def test_more_row_tiles_than_cta_pairs():
         assert_close(one[1], out[1][sr], f'graph {g} alone vs batched (pocket)', atol=3e-6, rtol=1e-5)
     want = egnn_oracle.denoiser_forward(cfg, sd, *single)
     assert_close(one[0], want[0], 'graph 99 vs oracle')
+
+
+@pytest.mark.parametrize('case', ['sin_h256_l2', 'sin_emb8_joint_h128_l2'])
+def test_golden_sin_embedding(case):
+    """sin_embedding=True (egnn_new.py:282-293; unused by the shipped configs): 2 x 12 sinusoidal distance features in the fp32
+    FFMA kernels; the tensor-core modes are rejected for such a module."""
+    from diffsbdd_b200 import _native
+    cfg, sd, inp, want, edges = load_golden(case)
+    net = make_net(cfg, sd)
+    assert net.math_mode == 0
+    got_a, got_r = run(net, inp)
+    assert net.last_num_edges == edges.shape[1]
+    assert_close(got_a, want[0], f'{case} ligand out')
+    assert_close(got_r, want[1], f'{case} pocket out')
+    with pytest.raises(_native.NativeError):
+        net.math_mode = '3xfp16'
+    net.math_mode = 'fp32'

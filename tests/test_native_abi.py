@@ -76,8 +76,9 @@ def test_edge_capacity_helper(lib):
 
 
 def test_unsupported_reference_options_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        EGNNDynamics(10, 10, 3, sin_embedding=True)
+    sin = EGNNDynamics(10, 10, 3, sin_embedding=True, hidden_nf=128)       # built since round 2 (fp32 FFMA kernels only)
+    assert sin.cfg.sin_embedding and sin.math_mode == 0
+    assert dict(sin.named_parameters())['egnn.e_block_0.gcl_0.edge_mlp.0.weight'].shape == (128, 2 * 128 + 24)
     assert EGNNDynamics(10, 10, 3, aggregation_method='mean').cfg.aggregation_method == 'mean'     # built since round 2
     with pytest.raises(ValueError):
         EGNNDynamics(10, 10, 3, aggregation_method='max')
