@@ -90,7 +90,9 @@ class EGNNDynamics(nn.Module):
         super().__init__()
         if mode != 'egnn_dynamics':
             if mode == 'gnn_dynamics':
-                raise NotImplementedError("mode='gnn_dynamics' is not built (unused by every shipped config)")
+                # not runnable in the reference either: its forward reads self.update_pocket_coords (dynamics.py:161), which
+                # only the egnn_dynamics branch of its constructor sets (dynamics.py:73) -> AttributeError on the first call
+                raise NotImplementedError("mode='gnn_dynamics' is not built (unused by every shipped config and broken in the reference)")
             raise Exception("Wrong mode %s" % mode)      # dynamics.py:144-145
         if aggregation_method not in ('sum', 'mean'):
             raise ValueError("aggregation_method must be 'sum' or 'mean' (egnn_new.py:321-335)")
