@@ -115,6 +115,12 @@ def workload_config(args, world=1):
     if args.workload == 'inpaint':
         cfg.update({'inpaint_timesteps': args.inpaint_timesteps, 'resamplings': args.resamplings, 'n_fixed': args.n_fixed,
                     'center': 'ligand'})
+    # the same text in every arm (the driver compares the `config` objects of the arms); what differs per arm is in `arm`
+    cfg.update({'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py), random-init of the named architecture',
+                'parallelism': (f'dp{world}: contiguous pocket shards per rank (diffsbdd_b200.distributed), no collective inside the '
+                                'loop, final all_gather of the ligands; the reference arm runs on rank 0 only'),
+                'l2': ('b200 arm: 256 MiB read+write flush before every timed step and e2e step; reference arms: none '
+                       '(CPU arm / eager GPU arm whose working set exceeds L2 per call)')})
     return cfg
 
 
@@ -296,9 +302,10 @@ def run_reference(args):
             times.append(dt)
         if i == 0 and args.warmup + args.steps > 1 and dt * (args.warmup + args.steps) > 240:
             per_step_budget = max(2.0, per_step_budget / 2)
-    cfgj = workload_config(args)
-    cfgj['reference_sample'] = 'bounded sample per step, extrapolated: ' + base['sample']
-    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+    cfgj = workload_config(args, int(os.environ.get('WORLD_SIZE', '1')))
+    arm = {'what': 'oracle port of the reference PyTorch op sequence on the host cores',
+           'reference_sample': 'bounded sample per step, extrapolated: ' + base['sample']}
+    line = {'impl': 'reference', 'arm': arm, 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * statistics.mean(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': cfgj, 'cpu_baseline': base,
@@ -330,9 +337,10 @@ def run_reference_gpu(args):
     n_calls = denoiser_calls(args)
     value = args.batch * args.n_lig / (per_call * n_calls)
     cfgj = workload_config(args)
-    cfgj['reference_sample'] = (f'full batch of {args.batch} pockets, {dyn.calls} denoiser calls in {sum(times):.2f} s = '
-                                f'{1e3 * per_call:.1f} ms/call (eager ATen ops incl. per-step host syncs), extrapolated x{n_calls} calls')
-    line = {'impl': 'reference-gpu', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': len(times),
+    arm = {'what': 'the reference PyTorch op sequence (oracle port) eager on cuda:0',
+           'reference_sample': (f'full batch of {args.batch} pockets, {dyn.calls} denoiser calls in {sum(times):.2f} s = '
+                                f'{1e3 * per_call:.1f} ms/call (eager ATen ops incl. per-step host syncs), extrapolated x{n_calls} calls')}
+    line = {'impl': 'reference-gpu', 'arm': arm, 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': len(times),
             'warmup': args.warmup, 'ms_per_step': 1e3 * per_call * n_calls, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfgj, 'clocks': clocks,
             'ms_per_denoiser_call': 1e3 * per_call,
@@ -562,14 +570,11 @@ def run_b200(args):
         if ddpm._graph_cache:
             engine = ('cuda_graph replay: denoiser + fused reverse update + fused RePaint iteration per (s, u)' if inpaint
                       else 'cuda_graph replay of one reverse step')
-        cfgj.update({'arithmetic': {0: 'fp32 FFMA', 7: '3xTF32 tcgen05', 15: '3xFP16 tcgen05'}.get(dyn.math_mode, str(dyn.math_mode)),
-                     'edges_last_call': e_last,
-                     'parallelism': f'dp{world} (contiguous pocket shards per rank via diffsbdd_b200.distributed, no collective '
-                                    'inside the loop, final all_gather of the ligands)',
-                     'l2': '256 MiB read+write flush before every timed step', 'loop_engine': engine,
-                     'weights': 'synthetic seed 0 (diffsbdd_b200/synthetic.py)'})
+        arm = {'what': 'diffsbdd_b200 (sm_100a kernels through the C ABI)',
+               'arithmetic': {0: 'fp32 FFMA', 7: '3xTF32 tcgen05', 15: '3xFP16 tcgen05'}.get(dyn.math_mode, str(dyn.math_mode)),
+               'edges_last_call': e_last, 'loop_engine': engine}
         per_rank_step = [m / args.steps for m in per_rank_ms]
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        line = {'arm': arm, 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfgj,
                 'ms_per_step_by_rank': {'min': min(per_rank_step), 'median': statistics.median(per_rank_step),
