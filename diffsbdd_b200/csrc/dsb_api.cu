@@ -645,7 +645,7 @@ using namespace dsb;
 extern "C" {
 
 const char* dsb_last_error(void) { return g_err; }
-const char* dsb_version(void) { return "diffsbdd_b200 0.2 (sm_100a: tcgen05 3xFP16/3xTF32 edge kernels and node GEMMs, fp32 FFMA kernels for other widths)"; }
+const char* dsb_version(void) { return "diffsbdd_b200 0.3 (sm_100a: tcgen05 3xFP16 CTA-pair edge kernels and fused node block kernel, 3xTF32 single-CTA kernels, fp32 FFMA kernels)"; }
 
 int dsb_param_count(const dsb_config* cfg) {
   if (int e = validate(cfg)) return e;
