@@ -286,12 +286,13 @@ __device__ __forceinline__ void silu4q(f32x2& u01, f32x2& u23) {
   upk2(mul2(u01, c), t0, t1); upk2(mul2(u23, c), t2, t3);
   const f32x2 d01 = add2(pk2(ex2_approx(fminf(t0, 31.f)), ex2_approx(fminf(t1, 31.f))), one);
   const f32x2 d23 = add2(pk2(ex2_approx(fminf(t2, 31.f)), ex2_approx(fminf(t3, 31.f))), one);
+  const f32x2 w01 = mul2(u01, d23), w23 = mul2(u23, d01);      // independent of the reciprocal: one multiply after it, not two
   float p0, p1;
   upk2(mul2(d01, d23), p0, p1);
   const float r = rcp_approx(p0 * p1);
-  const f32x2 rr = pk2(r * p1, r * p0);          // (1 / (d0 d2), 1 / (d1 d3))
-  u01 = mul2(u01, mul2(rr, d23));
-  u23 = mul2(u23, mul2(rr, d01));
+  const f32x2 rr = mul2(pk2(r, r), pk2(p1, p0));  // (1 / (d0 d2), 1 / (d1 d3)); broadcast and swapped pair are operand modifiers
+  u01 = mul2(w01, rr);
+  u23 = mul2(w23, rr);
 }
 #ifndef DSB_SILU_PAIR
 #define DSB_SILU_PAIR 3          // bit 0: producers, bit 1: epilogues of the tensor-core edge kernels use silu4

@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_node_block_kernel(TcBlockArg
             const float4 bb = __ldg(reinterpret_cast<const float4*>(g.b3 + cb * 32 + 4 * p8));
             f32x2 x01 = fma2(pk2(v[4 * p8], v[4 * p8 + 1]), ip, pk2(bb.x, bb.y));
             f32x2 x23 = fma2(pk2(v[4 * p8 + 2], v[4 * p8 + 3]), ip, pk2(bb.z, bb.w));
-            silu_pair<true>(x01, x23);
+            silu_pair<true, true>(x01, x23);
             float4 x;
             upk2(x01, x.x, x.y); upk2(x23, x.z, x.w);
             store_piece<true>(st, myrow, cb & 1, p8, x);
@@ -1635,7 +1635,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     const float* ps[4] = {Pt, Pt, Pt, Pt};     // the four sender rows
     int pty[4] = {0, 0, 0, 0};
     const int soff = nm * H;                   // sender block follows the nm receiver blocks
-    float4 ga, gb[4], ga2, gb2[4];
+    float4 GA[2], GB[2][4];                    // two gather register sets: chunk kc computes from set kc & 1 while the other one fills
     auto setup_unit = [&](int j) {             // row pointers and scalars of unit j; returns its MLP index
       int m;
       unit_tile(j, m);
@@ -1661,7 +1661,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     long long t0 = 0, t1 = 0, t2 = 0, acc_wait = 0, acc_comp = 0, acc_fence = 0;
     const long long pp0 = pprof ? tc_clock() : 0;
     int m = setup_unit(0);
-    issue(0, ga, gb);
+    issue(0, GA[0], GB[0]);
     for (int j = 0; j < n_my; ++j) {
       const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H;
       const float* tbm = TB ? a.tb[m] + 4 * pc : nullptr;
@@ -1672,11 +1672,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         if (pprof) t0 = tc_clock();
         mbar_wait(&ctl->empty[s], ((gc >> 1) & 1) ^ 1);      // stage released by the MMAs that read it two chunks ago
         if (pprof) { t1 = tc_clock(); acc_wait += t1 - t0; }
+        float4& ga = GA[kc & 1];                             // (static indices: the chunk loop is unrolled, no register copies)
+        float4 (&gb)[4] = GB[kc & 1];
 #pragma unroll
         for (int h = 0; h < HPC; ++h) {
           const int hf = kc * HPC + h;
           const bool last_half = (h == HPC - 1);
-          if (last_half && kc + 1 < chunks && !(dbg & 2)) issue(hf + 1, ga2, gb2);          // (ii)
+          if (last_half && kc + 1 < chunks && !(dbg & 2)) issue(hf + 1, GA[(kc & 1) ^ 1], GB[(kc & 1) ^ 1]);          // (ii)
           if (!(dbg & 2)) {
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
@@ -1703,15 +1705,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         if (lane == 0) arrive_full_x(s);
         ++gc;
         if (pprof) acc_fence += tc_clock() - t2;
-        if (kc + 1 < chunks) {
-          ga = ga2;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) gb[i] = gb2[i];
-        }
       }
       if (j + 1 < n_my) {                                                                      // (iii)
         m = setup_unit(j + 1);
-        if (!(dbg & 2)) issue(0, ga, gb);
+        if (!(dbg & 2)) issue(0, GA[0], GB[0]);
       }
       if (pprof) {
         atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU + split + swizzled stores

@@ -266,14 +266,24 @@ __device__ __forceinline__ void store_split(char* a_hi, char* a_lo, int row, int
   *reinterpret_cast<float4*>(a_lo + off) = l;
 }
 
+// Residual of the 3xFP16 split, x - float(hi), for a packed pair of fp16 hi parts: one mixed-precision FMA per value
+// (fma.rn.f32.f16 = FHFMA: hi * (-1) + x, exact) instead of a half->float conversion plus a subtraction.  Same bits as
+// x - __half2float(hi): the difference is representable in fp32.
+__device__ __forceinline__ void residual_f16(uint32_t hi2, float x0, float x1, float& r0, float& r1) {
+  asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; fma.rn.f32.f16 %0, l, %3, %4; fma.rn.f32.f16 %1, h, %3, %5;}"
+      : "=f"(r0), "=f"(r1) : "r"(hi2), "h"((unsigned short)0xBC00), "f"(x0), "f"(x1));
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 // 3xFP16 producer helper: 8 consecutive k-values (two float4, already multiplied by X_SCALE) -> 16-byte chunk c16 of the
 // row in the hi and lo tiles.  x_h = fp16_rn(x), x_l = fp16_rn(x - x_h): 22 significand bits while x_l is a normal fp16.
 __device__ __forceinline__ void store_split_f16(char* a_hi, char* a_lo, int row, int c16, float4 v0, float4 v1) {
   const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
   const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
-  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-  const __half2 l0 = __floats2half2_rn(v0.x - f0.x, v0.y - f0.y), l1 = __floats2half2_rn(v0.z - f1.x, v0.w - f1.y);
-  const __half2 l2 = __floats2half2_rn(v1.x - f2.x, v1.y - f2.y), l3 = __floats2half2_rn(v1.z - f3.x, v1.w - f3.y);
+  float r0, r1, r2, r3, r4, r5, r6, r7;
+  residual_f16(h2_bits(h0), v0.x, v0.y, r0, r1); residual_f16(h2_bits(h1), v0.z, v0.w, r2, r3);
+  residual_f16(h2_bits(h2), v1.x, v1.y, r4, r5); residual_f16(h2_bits(h3), v1.z, v1.w, r6, r7);
+  const __half2 l0 = __floats2half2_rn(r0, r1), l1 = __floats2half2_rn(r2, r3);
+  const __half2 l2 = __floats2half2_rn(r4, r5), l3 = __floats2half2_rn(r6, r7);
   const uint32_t off = sw128_offset(row, c16);
   uint4 hv, lv;
   hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -293,8 +303,9 @@ template <bool F16>
 __device__ __forceinline__ void store_piece(char* st, int row, int half, int p, float4 v) {
   if constexpr (F16) {
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    float r0, r1, r2, r3;
+    residual_f16(h2_bits(h0), v.x, v.y, r0, r1); residual_f16(h2_bits(h1), v.z, v.w, r2, r3);
+    const __half2 l0 = __floats2half2_rn(r0, r1), l1 = __floats2half2_rn(r2, r3);
     const uint32_t off = sw128_offset(row, (half & 1) * 4 + (p >> 1)) + (p & 1) * 8;
     uint2 hv, lv;
     hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -326,10 +337,13 @@ __device__ __forceinline__ void store_pair(char* dst, f32x2 u01, f32x2 u23) {
     const float2 f0 = make_float2(t0, t1), f1 = make_float2(t2, t3);
 #else
     const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
 #endif
     float l0, l1, l2, l3;
+#if DSB_SPLIT_TRUNC
     upk2(sub2_(u01, pk2(f0.x, f0.y)), l0, l1); upk2(sub2_(u23, pk2(f1.x, f1.y)), l2, l3);
+#else
+    residual_f16(h2_bits(h0), x0, x1, l0, l1); residual_f16(h2_bits(h1), x2, x3, l2, l3);
+#endif
     const __half2 q0 = __floats2half2_rn(l0, l1), q1 = __floats2half2_rn(l2, l3);
     uint2 hv, lv;
     hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
