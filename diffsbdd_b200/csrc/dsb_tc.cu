@@ -1224,6 +1224,10 @@ __global__ void __launch_bounds__(PG_THREADS, 1) tc_pair_gemm_kernel(TcPairGemmA
 #define DSB_E2_UNROLL 2
 #endif
 constexpr int kE1Unroll = DSB_E1_UNROLL, kE2Unroll = DSB_E2_UNROLL;
+#ifndef DSB_EARLY_UNIT
+#define DSB_EARLY_UNIT 0        // edge producers: 1 = next unit's first gathers issued during the last half of the current unit
+                                // (measured: GCL 133.2 vs 132.6 us, coord 63.8 vs 61.7 us per launch with 0 -> off)
+#endif
 #ifndef DSB_RED_PAIR
 #define DSB_RED_PAIR 1          // GCL pass 2: one RED per chunk PAIR of the same receiver
 #endif
@@ -1636,7 +1640,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     int pty[4] = {0, 0, 0, 0};
     const int soff = nm * H;                   // sender block follows the nm receiver blocks
     float4 GA[2], GB[2][4];                    // two gather register sets: chunk kc computes from set kc & 1 while the other one fills
-    auto setup_unit = [&](int j) {             // row pointers and scalars of unit j; returns its MLP index
+    auto setup_ptrs = [&](int j) {             // row pointers of unit j (gathers); returns its MLP index
       int m;
       unit_tile(j, m);
       const int par = j % NSCAL;
@@ -1644,13 +1648,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
       const int moff = m * H;                  // column offset of the unit's MLP inside the receiver / sender blocks
       pr = Pt + (size_t)max(ex->row[par][r0], 0) * a.ldp + moff;
 #pragma unroll
+      for (int i = 0; i < 4; ++i) ps[i] = Pt + (size_t)ex->col[par][r0 + i] * a.ldp + (soff + moff);
+      return m;
+    };
+    auto setup_scal = [&](int j) {             // per-row scalars of unit j (after setup_ptrs(j): the set has arrived)
+      const int par = j % NSCAL;
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
-        ps[i] = Pt + (size_t)ex->col[par][r0 + i] * a.ldp + (soff + moff);
         pd2[i] = ex->d2[par][r0 + i]; pd0[i] = ex->d0[par][r0 + i];
         if (TB) pty[i] = ex->type[par][r0 + i] * H;
       }
-      return m;
     };
+    // (iii) early (DSB_EARLY_UNIT, off): with an even number of chunks the register set the next unit's chunk 0 reads (set 0) is
+    // idle during the last chunk (set 1), and the row pointers are dead after the last half's loads, so the next unit's first
+    // gathers could go out a whole half before the unit boundary instead of right in front of their first use (6 % of the
+    // producers' samples are that stall) - but the producers have slack (they wait 17 % of their time for the ring) and the
+    // longer live ranges cost more than the stall: slower when measured.
+    constexpr bool kEarlyUnit = DSB_EARLY_UNIT && (chunks % 2 == 0);
     const bool no_gather = (dbg & 64) != 0;        // instrumented builds only: operands from registers instead of L2
     auto ld4 = [&](const float* p) { return no_gather ? make_float4(0.1f, -0.2f, 0.3f, 0.05f) : *reinterpret_cast<const float4*>(p); };
     auto issue = [&](int hf, float4& xa, float4 (&xb)[4]) {
@@ -1660,7 +1674,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
     };
     long long t0 = 0, t1 = 0, t2 = 0, acc_wait = 0, acc_comp = 0, acc_fence = 0;
     const long long pp0 = pprof ? tc_clock() : 0;
-    int m = setup_unit(0);
+    int m = setup_ptrs(0), m_next = 0;
+    setup_scal(0);
     issue(0, GA[0], GB[0]);
     for (int j = 0; j < n_my; ++j) {
       const float* wr = ex->vec[m] + 4 * pc; const float* wr0 = wr + H;
@@ -1679,6 +1694,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
           const int hf = kc * HPC + h;
           const bool last_half = (h == HPC - 1);
           if (last_half && kc + 1 < chunks && !(dbg & 2)) issue(hf + 1, GA[(kc & 1) ^ 1], GB[(kc & 1) ^ 1]);          // (ii)
+          if (kEarlyUnit && last_half && kc + 1 == chunks && j + 1 < n_my) {                                         // (iii) early
+            m_next = setup_ptrs(j + 1);
+            if (!(dbg & 2)) issue(0, GA[0], GB[0]);
+          }
           if (!(dbg & 2)) {
             const float4 r4 = *reinterpret_cast<const float4*>(wr + hf * TKC);
             const float4 r04 = *reinterpret_cast<const float4*>(wr0 + hf * TKC);
@@ -1707,8 +1726,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) tc_edge_kernel(TcEdgeArgs a) 
         if (pprof) acc_fence += tc_clock() - t2;
       }
       if (j + 1 < n_my) {                                                                      // (iii)
-        m = setup_unit(j + 1);
-        if (!(dbg & 2)) issue(0, GA[0], GB[0]);
+        if (kEarlyUnit) m = m_next;
+        else {
+          m = setup_ptrs(j + 1);
+          if (!(dbg & 2)) issue(0, GA[0], GB[0]);
+        }
+        setup_scal(j + 1);
       }
       if (pprof) {
         atomicAdd(&g_tc_prof[9], (unsigned long long)acc_comp);    // gather wait + pre-activation + SiLU + split + swizzled stores
