@@ -249,59 +249,78 @@ def _reference_run(args, ddpm, cfg, density, nb, sub_steps, device, seed=3):
     return time.perf_counter() - t0
 
 
+class _CpuReference:
+    """The CPU port on a BOUNDED sample of the workload: the first ``nb`` pockets of the batch (CPU cost is linear in the
+    number of pockets: graphs are independent), 1 reverse step + the final p(x|z0) call per repetition; atoms/s
+    extrapolated to the full loop (every denoiser call of the loop has the same cost; the O(N) update/blend ops between
+    calls are <1 % of a call on the CPU).  Built once per process; the torch thread count is calibrated once, under a
+    time cap (most likely candidates first)."""
+
+    def __init__(self, args, sub_batch=None, calibrate_s=15.0):
+        self.args = args
+        self.ddpm, self.dyn, self.cfg, self.density = _reference_ddpm(args, 'cpu')
+        self.cores = os.cpu_count() or 1
+        self.nb = min(sub_batch or 8, args.batch)
+        torch.manual_seed(0)
+        self.cands = [c for c in (16, 32, 8, 64, self.cores) if c <= self.cores] or [self.cores]
+        self.tried = []
+        best_t = None
+        t_cal0 = time.perf_counter()
+        for th in dict.fromkeys(self.cands):
+            torch.set_num_threads(th)
+            if not self.tried:
+                self.one()                                       # first touch: allocator, oneDNN primitives
+            t = self.one()
+            self.tried.append(th)
+            if best_t is None or t < best_t:
+                self.threads, best_t = th, t
+            if time.perf_counter() - t_cal0 > calibrate_s:
+                break
+        torch.set_num_threads(self.threads)
+
+    def one(self):                                               # 2 denoiser calls
+        return _reference_run(self.args, self.ddpm, self.cfg, self.density, self.nb, 1, 'cpu')
+
+    def sample(self, budget_s):
+        args = self.args
+        self.dyn.calls = 0
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 1 or (time.perf_counter() - t0 < budget_s and reps < 50):
+            self.one()
+            reps += 1
+        dt = time.perf_counter() - t0
+        per_call = dt / self.dyn.calls
+        n_calls = denoiser_calls(args)
+        atoms = self.nb * args.n_lig
+        return {'value': atoms / (per_call * n_calls), 'unit': UNIT, 'cores': self.threads, 'kind': 'port',
+                'sample': (f'oracle port of the reference PyTorch path (oracle/egnn_oracle.py + eager reference-order DDPM '
+                           f'loop) on the first {self.nb} of the {args.batch} pockets, {self.dyn.calls} denoiser calls in '
+                           f'{dt:.1f} s = {per_call:.2f} s/call, extrapolated x{n_calls} calls; torch threads calibrated '
+                           f'over {self.tried} of {self.cores} host cores -> {self.threads}'),
+                'seconds_per_denoiser_call': per_call, 'host_cores': self.cores, 'torch_threads': self.threads,
+                'sample_pockets': self.nb}, dt, self.dyn.calls
+
+
 def cpu_reference_sample(args, budget_s, sub_batch=None):
-    """Times the CPU port on a BOUNDED sample of the same workload: the first ``nb`` pockets of the batch (CPU cost is
-    linear in the number of pockets: graphs are independent), 1 reverse step + the final p(x|z0) call, repeated until
-    ~budget_s; atoms/s extrapolated to the full loop (every denoiser call of the loop has the same cost; the O(N)
-    update/blend ops between calls are <1 % of a call on the CPU).  The torch thread count is calibrated first."""
-    ddpm, dyn, cfg, density = _reference_ddpm(args, 'cpu')
-    cores = os.cpu_count() or 1
-    nb = min(sub_batch or 8, args.batch)
-    torch.manual_seed(0)
-    one = lambda: _reference_run(args, ddpm, cfg, density, nb, 1, 'cpu')      # 2 denoiser calls
-    best_threads, best_t = cores, None
-    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
-    t_cal0 = time.perf_counter()
-    for th in cands:
-        torch.set_num_threads(th)
-        one()
-        t = one()
-        if best_t is None or t < best_t:
-            best_threads, best_t = th, t
-        if time.perf_counter() - t_cal0 > budget_s:
-            break
-    torch.set_num_threads(best_threads)
-    dyn.calls = 0
-    t0 = time.perf_counter()
-    reps = 0
-    while reps < 1 or (time.perf_counter() - t0 < 0.5 * budget_s and reps < 50):
-        one()
-        reps += 1
-    dt = time.perf_counter() - t0
-    per_call = dt / dyn.calls
-    n_calls = denoiser_calls(args)
-    atoms = nb * args.n_lig
-    return {'value': atoms / (per_call * n_calls), 'unit': UNIT, 'cores': best_threads, 'kind': 'port',
-            'sample': (f'oracle port of the reference PyTorch path (oracle/egnn_oracle.py + eager reference-order DDPM '
-                       f'loop) on the first {nb} of the {args.batch} pockets, {dyn.calls} denoiser calls in {dt:.1f} s = '
-                       f'{per_call:.2f} s/call, extrapolated x{n_calls} calls; torch threads calibrated over '
-                       f'{cands} of {cores} host cores -> {best_threads}'),
-            'seconds_per_denoiser_call': per_call, 'host_cores': cores, 'torch_threads': best_threads,
-            'sample_pockets': nb}, dt, dyn.calls
+    return _CpuReference(args, sub_batch).sample(0.5 * budget_s)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    t_all = time.perf_counter()
+    ref = _CpuReference(args)
+    n_it = args.warmup + args.steps
+    # the whole run stays within ~3 minutes: equal shares of what the calibration left, at least one repetition per step
     times, base = [], None
-    per_step_budget = max(4.0, min(args.cpu_sample_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    for i in range(args.warmup + args.steps):
-        base, dt, calls = cpu_reference_sample(args, per_step_budget)
+    for i in range(n_it):
+        left = 170.0 - (time.perf_counter() - t_all)
+        per_step = max(0.0, min(0.5 * args.cpu_sample_seconds, left / max(1, n_it - i)))
+        base, dt, calls = ref.sample(per_step)
         if i >= args.warmup:
             times.append(dt)
-        if i == 0 and args.warmup + args.steps > 1 and dt * (args.warmup + args.steps) > 240:
-            per_step_budget = max(2.0, per_step_budget / 2)
     cfgj = workload_config(args, int(os.environ.get('WORLD_SIZE', '1')))
     arm = {'what': 'oracle port of the reference PyTorch op sequence on the host cores',
            'reference_sample': 'bounded sample per step, extrapolated: ' + base['sample']}
