@@ -1,7 +1,7 @@
 """Counts the SASS mnemonics that prove which hardware path each hot kernel of libdiffsbdd_b200.so takes (tcgen05 MMAs incl. the
 cta_group::2 form, TMEM loads/stores, bulk copies, multicast commits, cluster barriers, packed fp32, vector REDs).
 
-    python profiles/sass_summary.py > profiles/r2c_sass.txt"""
+    python profiles/sass_summary.py > profiles/r2e_sass.txt"""
 import collections
 import os
 import re
@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffsbdd_b200 import _build  # noqa: E402
 
 KEYS = ['UTCHMMA.2CTA', 'UTCHMMA', 'UTCBAR.2CTA.MULTICAST', 'UTCBAR', 'LDTM', 'STTM', 'UBLKCP', 'UTMALDG', 'UCGABAR_ARV', 'SYNCS', 'FENCE.VIEW.ASYNC',
-        'USETMAXREG', 'MUFU.EX2', 'MUFU.RCP', 'FFMA2', 'FADD2', 'FMUL2', 'F2FP', 'REDG.E.ADD.F32x4', 'REDG', 'LDG.E.128', 'STS.64', 'STS.128', 'LDS.128']
+        'USETMAXREG', 'FHFMA', 'HADD2.F32', 'MUFU.EX2', 'MUFU.RCP', 'FFMA2', 'FADD2', 'FMUL2', 'F2FP', 'REDG.E.ADD.F32x4', 'REDG', 'LDG.E.128', 'STS.64', 'STS.128', 'LDS.128']
 WANT = ['tc_edge_kernelILb0ELb1ELi256ELb0ELb1', 'tc_edge_kernelILb1ELb1ELi256ELb0ELb1', 'tc_edge_kernelILb0ELb1ELi256ELb0ELb0',
         'tc_node_block_kernelILi256', 'tc_pair_gemm_kernelILi256', 'tc_node_gemm_kernelILb1ELi256', 'tc_node_mlp_kernelILb1ELi256']
 out = subprocess.run(['cuobjdump', '-sass', _build.LIB_PATH], capture_output=True, text=True).stdout
